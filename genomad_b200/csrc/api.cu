@@ -1,0 +1,594 @@
+// libgnm.so -- C ABI (include/gnm.h) over the sm_100a kernels of the geNomad nn-classification path.
+// Host side of the library: weight re-packing, workspace, TMA descriptors, stage orchestration.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gnm.h"
+#include "common.cuh"
+#include "encode.cuh"
+#include "conv_tc.cuh"
+#include "conv_ref.cuh"
+#include "igloo.cuh"
+#include "dense.cuh"
+
+using namespace gnm;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+
+#define GNM_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(std::string(#expr) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ \
+                  ":" + std::to_string(__LINE__) + ")");                                     \
+  } while (0)
+
+extern "C" const char* gnm_last_error(void) { return g_err.c_str(); }
+extern "C" const char* gnm_version(void) { return "libgnm 0.1 (sm_100a, tcgen05 fp16x3-split)"; }
+
+// ------------------------------------------------------------------------------------------------
+struct StageTimer {
+  std::vector<const char*> names;
+  std::vector<cudaEvent_t> events;   // events[i] recorded BEFORE stage i; last one after the final stage
+};
+
+struct gnm_handle {
+  int device = 0;
+  int max_batch = 0;
+  int num_sms = 0;
+  long long launches = 0;
+  // options
+  int conv_impl = 0;        // 0 tcgen05, 1 fp32 validation kernels
+  int desc_base_mode = 0;
+  int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
+  int profile_stages = 0;
+  // weights on device
+  float* conv1_table = nullptr; float* conv1_bias = nullptr;
+  __half* wpack[3] = {nullptr, nullptr, nullptr};   // conv2(+wv0), conv3, wv1 -- TMA stage order
+  float* conv_bias[2] = {nullptr, nullptr};
+  float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
+  float* wv32[2] = {nullptr, nullptr};
+  float* wf[2] = {nullptr, nullptr}; int32_t* patches[2] = {nullptr, nullptr};
+  float* wbias[2] = {nullptr, nullptr}; float* wqk[2] = {nullptr, nullptr};
+  float* d0w = nullptr; float* d0b = nullptr; float* bn0_scale = nullptr; float* bn0_shift = nullptr;
+  float* d1w = nullptr; float* d1b = nullptr; float* bn1_scale = nullptr; float* bn1_shift = nullptr;
+  float* d2w = nullptr; float* d2b = nullptr;
+  // workspace
+  __half* ybuf[2] = {nullptr, nullptr};
+  float* q[2] = {nullptr, nullptr};
+  float* mpi[2] = {nullptr, nullptr};
+  float* logits = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
+  float* scratch32 = nullptr;                        // validation path only, allocated lazily
+  uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
+  float* out_stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
+  DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
+  CUtensorMap tm_act[2];
+  CUtensorMap tm_w[3];
+  int last_n = 0;
+  StageTimer timer;
+  std::vector<float> stage_ms;
+  std::vector<void*> allocs;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int dev_upload(gnm_handle* h, T** dst, const T* src, size_t count) {
+  GNM_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), count * sizeof(T)));
+  h->allocs.push_back(*dst);
+  GNM_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+template <class T>
+static int dev_alloc(gnm_handle* h, T** dst, size_t count) {
+  GNM_CUDA(cudaMalloc(reinterpret_cast<void**>(dst), count * sizeof(T)));
+  h->allocs.push_back(*dst);
+  return 0;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(PFN_encodeTiled* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  GNM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !p) return fail("cuTensorMapEncodeTiled not available from the driver");
+  *fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return 0;
+}
+
+// activations [n][5997][256] fp16; box = 64 channels x 136 rows x 1 window, 128B swizzle, OOB rows -> 0
+static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, __half* base, int n_windows) {
+  cuuint64_t dims[3] = {kRowHalfs, kTok, static_cast<cuuint64_t>(n_windows)};
+  cuuint64_t strides[2] = {kRowHalfs * sizeof(__half), static_cast<cuuint64_t>(kTok) * kRowHalfs * sizeof(__half)};
+  cuuint32_t box[3] = {64, kSlabRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activations) failed: " + std::to_string(int(r)));
+  return 0;
+}
+// packed weights [stages*128 rows][64] fp16; box = 64 x 128
+static int make_w_map(PFN_encodeTiled enc, CUtensorMap* tm, __half* base, int n_stages) {
+  cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(n_stages) * 128};
+  cuuint64_t strides[1] = {64 * sizeof(__half)};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
+  return 0;
+}
+
+// One 16 KB TMA stage: B[n][kk] = part(W[k = kh*64 + kk][n]), part = hi or lo of the fp16 split.
+static void pack_stage(std::vector<__half>& dst, const float* Wkn /* [128 k][128 n] */, int w_lo, int kh) {
+  for (int n = 0; n < kC; ++n)
+    for (int kk = 0; kk < 64; ++kk) {
+      const float x = Wkn[static_cast<size_t>(kh * 64 + kk) * kC + n];
+      const __half hi = __float2half_rn(x);
+      const __half lo = __float2half_rn(x - __half2float(hi));
+      dst.push_back(w_lo ? lo : hi);
+    }
+}
+static void pack_matrix_stages(std::vector<__half>& dst, const float* Wkn) {   // order: (hi,k0) (hi,k1) (lo,k0) (lo,k1)
+  for (int w_lo = 0; w_lo < 2; ++w_lo)
+    for (int kh = 0; kh < 2; ++kh) pack_stage(dst, Wkn, w_lo, kh);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_handle** out) {
+  if (!w || !out) return fail("gnm_create: null argument");
+  if (max_batch < 1) return fail("gnm_create: max_batch must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("gnm_create: no CUDA device available (libgnm has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("gnm_create: bad device index");
+  cudaDeviceProp prop;
+  GNM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(std::string("gnm_create: device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                ", this library is built for sm_100a (B200) only");
+  GNM_CUDA(cudaSetDevice(device));
+  gnm_handle* h = new gnm_handle();
+  h->device = device;
+  h->max_batch = max_batch;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;   // so the caller can gnm_destroy() after a partial failure
+
+  // ---- validate patch indices (a bad index would read out of bounds)
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < kPatches * kPatchLen; ++i)
+      if (w->igloo[s].patches[i] < 0 || w->igloo[s].patches[i] >= kTok)
+        return fail("gnm_create: patch index out of range [0, 5997)");
+
+  // ---- first layer table + bias
+  if (dev_upload(h, &h->conv1_table, w->conv1_kernel, static_cast<size_t>(kTaps) * kVocab * kC)) return 1;
+  if (dev_upload(h, &h->conv1_bias, w->conv1_bias, kC)) return 1;
+
+  // ---- tensor-core weight packs (consumption order of conv_tc_kernel)
+  {
+    const float* convw[2] = {w->conv2_kernel, w->conv3_kernel};
+    for (int L = 0; L < 2; ++L) {
+      std::vector<__half> pk;
+      pk.reserve(static_cast<size_t>(28) * 128 * 64);
+      for (int tap = 0; tap < kTaps; ++tap) pack_matrix_stages(pk, convw[L] + static_cast<size_t>(tap) * kC * kC);
+      if (L == 0) pack_matrix_stages(pk, w->igloo[0].w_v);   // conv2 kernel also projects its INPUT (y1) with w_v#0
+      if (dev_upload(h, &h->wpack[L], pk.data(), pk.size())) return 1;
+      if (dev_upload(h, &h->conv_w32[L], convw[L], static_cast<size_t>(kTaps) * kC * kC)) return 1;
+    }
+    std::vector<__half> pk;
+    pack_matrix_stages(pk, w->igloo[1].w_v);
+    if (dev_upload(h, &h->wpack[2], pk.data(), pk.size())) return 1;
+    if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
+    if (dev_upload(h, &h->conv_bias[1], w->conv3_bias, kC)) return 1;
+  }
+  // ---- IGLOO weights
+  for (int s = 0; s < 2; ++s) {
+    const gnm_igloo_weights& g = w->igloo[s];
+    std::vector<float> wf(static_cast<size_t>(kPatches) * kPatchLen * kC);
+    for (int p = 0; p < kPatches; ++p)
+      for (int k = 0; k < kPatchLen; ++k)
+        for (int c = 0; c < kC; ++c) {
+          const size_t i = (static_cast<size_t>(p) * kPatchLen + k) * kC + c;
+          wf[i] = g.w_mult[i] * g.w_summer[k * kC + c];
+        }
+    if (dev_upload(h, &h->wf[s], wf.data(), wf.size())) return 1;
+    if (dev_upload(h, &h->patches[s], g.patches, static_cast<size_t>(kPatches) * kPatchLen)) return 1;
+    if (dev_upload(h, &h->wbias[s], g.w_bias, kPatches)) return 1;
+    if (dev_upload(h, &h->wqk[s], g.w_qk, static_cast<size_t>(kPatches) * kPooled)) return 1;
+    if (dev_upload(h, &h->wv32[s], g.w_v, static_cast<size_t>(kC) * kC)) return 1;
+  }
+  // ---- head: keras BN inference form  x * inv + (beta - mean * inv),  inv = gamma * rsqrt(var + eps)
+  {
+    auto bn = [&](const gnm_bn_weights& b, float** scale, float** shift) -> int {
+      std::vector<float> sc(kHidden), sh(kHidden);
+      for (int i = 0; i < kHidden; ++i) {
+        const float inv = b.gamma[i] * (1.0f / std::sqrt(b.moving_variance[i] + 1e-3f));
+        sc[i] = inv;
+        sh[i] = b.beta[i] - b.moving_mean[i] * inv;
+      }
+      if (dev_upload(h, scale, sc.data(), kHidden)) return 1;
+      return dev_upload(h, shift, sh.data(), kHidden);
+    };
+    if (dev_upload(h, &h->d0w, w->dense0_kernel, static_cast<size_t>(256) * kHidden)) return 1;
+    if (dev_upload(h, &h->d0b, w->dense0_bias, kHidden)) return 1;
+    if (bn(w->bn0, &h->bn0_scale, &h->bn0_shift)) return 1;
+    if (dev_upload(h, &h->d1w, w->dense1_kernel, static_cast<size_t>(kHidden) * kHidden)) return 1;
+    if (dev_upload(h, &h->d1b, w->dense1_bias, kHidden)) return 1;
+    if (bn(w->bn1, &h->bn1_scale, &h->bn1_shift)) return 1;
+    if (dev_upload(h, &h->d2w, w->dense2_kernel, static_cast<size_t>(kHidden) * 3)) return 1;
+    if (dev_upload(h, &h->d2b, w->dense2_bias, 3)) return 1;
+  }
+  // ---- workspace
+  const size_t mb = static_cast<size_t>(max_batch);
+  for (int i = 0; i < 2; ++i) {
+    if (dev_alloc(h, &h->ybuf[i], mb * kTok * kRowHalfs)) return 1;
+    if (dev_alloc(h, &h->q[i], mb * kPooled * kC)) return 1;
+    if (dev_alloc(h, &h->mpi[i], mb * kPatches)) return 1;
+    if (dev_alloc(h, &h->in_stage[i], mb * kWindow)) return 1;
+    if (dev_alloc(h, &h->out_stage[i], mb * 3)) return 1;
+    GNM_CUDA(cudaEventCreateWithFlags(&h->in_ready[i], cudaEventDisableTiming));
+    GNM_CUDA(cudaEventCreateWithFlags(&h->in_free[i], cudaEventDisableTiming));
+  }
+  if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
+  if (dev_alloc(h, &h->h0, mb * 256)) return 1;
+  if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
+  if (dev_alloc(h, &h->h2, mb * kHidden)) return 1;
+  GNM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  GNM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+  GNM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->status), sizeof(DeviceStatus), cudaHostAllocMapped));
+  std::memset(h->status, 0, sizeof(DeviceStatus));
+
+  // ---- TMA descriptors
+  PFN_encodeTiled enc = nullptr;
+  if (get_encode_fn(&enc)) return 1;
+  for (int i = 0; i < 2; ++i)
+    if (make_act_map(enc, &h->tm_act[i], h->ybuf[i], max_batch)) return 1;
+  if (make_w_map(enc, &h->tm_w[0], h->wpack[0], 28)) return 1;
+  if (make_w_map(enc, &h->tm_w[1], h->wpack[1], 24)) return 1;
+  if (make_w_map(enc, &h->tm_w[2], h->wpack[2], 4)) return 1;
+
+  // ---- opt in to large dynamic shared memory
+  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
+  GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
+  GNM_CUDA(cudaFuncSetAttribute(patch_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+  GNM_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int gnm_destroy(gnm_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->scratch32) cudaFree(h->scratch32);
+  for (int i = 0; i < 2; ++i) {
+    if (h->in_ready[i]) cudaEventDestroy(h->in_ready[i]);
+    if (h->in_free[i]) cudaEventDestroy(h->in_free[i]);
+  }
+  for (cudaEvent_t e : h->timer.events) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+  if (h->status) cudaFreeHost(h->status);
+  delete h;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_launch(gnm_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + " launch failed: " + cudaGetErrorString(e));
+  h->launches++;
+  return 0;
+}
+
+static void timer_mark(gnm_handle* h, const char* name, cudaStream_t st) {
+  if (!h->profile_stages) return;
+  StageTimer& t = h->timer;
+  const size_t i = t.names.size();
+  if (t.events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); t.events.push_back(e); }
+  cudaEventRecord(t.events[i], st);
+  t.names.push_back(name);
+}
+
+static int launch_conv_tc(gnm_handle* h, int which, int in_buf, int n, cudaStream_t st) {
+  ConvTcParams p;
+  p.n_tiles = n * kTilesPerWin;
+  p.desc_base_mode = h->desc_base_mode;
+  p.status = h->status;
+  const int grid = std::min(h->num_sms, p.n_tiles);
+  if (which == 0) {          // conv2: y[in] -> y[1-in], q0 from the input
+    p.bias = h->conv_bias[0]; p.y_out = h->ybuf[1 - in_buf]; p.q_out = h->q[0];
+    conv_tc_kernel<6, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[0], p);
+  } else if (which == 1) {   // conv3
+    p.bias = h->conv_bias[1]; p.y_out = h->ybuf[1 - in_buf]; p.q_out = nullptr;
+    conv_tc_kernel<6, false><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[1], p);
+  } else {                   // w_v#1 + max-pool on y3
+    p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[1];
+    conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[2], p);
+  }
+  return check_launch(h, "conv_tc_kernel");
+}
+
+static int ensure_scratch(gnm_handle* h) {
+  if (h->scratch32) return 0;
+  GNM_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->scratch32), static_cast<size_t>(h->max_batch) * kTok * kC * sizeof(float)));
+  return 0;
+}
+
+static int launch_conv_ref(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t st) {
+  if (ensure_scratch(h)) return 1;
+  dim3 grid((kTok + kRefPos - 1) / kRefPos, n);
+  conv_ref_kernel<6, true><<<grid, kRefThreads, ref_smem_bytes<6>(), st>>>(h->ybuf[in_buf], h->conv_w32[layer],
+                                                                          h->conv_bias[layer], h->scratch32);
+  if (check_launch(h, "conv_ref_kernel")) return 1;
+  const size_t rows = static_cast<size_t>(n) * kTok;
+  const size_t threads = rows * (kC / 4);
+  split_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(h->scratch32, h->ybuf[1 - in_buf], rows);
+  return check_launch(h, "split_rows_kernel");
+}
+static int launch_wv_ref(gnm_handle* h, int s, int in_buf, int n, cudaStream_t st) {
+  if (ensure_scratch(h)) return 1;
+  dim3 grid((kTok + kRefPos - 1) / kRefPos, n);
+  conv_ref_kernel<1, false><<<grid, kRefThreads, ref_smem_bytes<1>(), st>>>(h->ybuf[in_buf], h->wv32[s], nullptr, h->scratch32);
+  if (check_launch(h, "conv_ref_kernel<1>")) return 1;
+  const size_t total = static_cast<size_t>(n) * kPooled * kC;
+  maxpool8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(h->scratch32, h->q[s], n);
+  return check_launch(h, "maxpool8_kernel");
+}
+
+static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
+  // enough window chunks to give every SM a few CTAs, while each CTA amortises its 64 KB weight stage
+  int chunks = std::max(1, std::min(n, (4 * h->num_sms + kGatherGroups - 1) / kGatherGroups));
+  const int wpc = (n + chunks - 1) / chunks;
+  chunks = (n + wpc - 1) / wpc;
+  dim3 grid(kGatherGroups, chunks);
+  patch_gather_kernel<<<grid, kGatherThreads, kGatherSmem, st>>>(h->ybuf[buf], h->wf[s], h->patches[s], h->wbias[s],
+                                                                h->mpi[s], n, wpc);
+  return check_launch(h, "patch_gather_kernel");
+}
+
+static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
+                        int K, const float* bias, const float* scale, const float* shift, int relu, cudaStream_t st) {
+  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
+  sgemm_epi_kernel<<<grid, kGemmThreads, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+  return check_launch(h, "sgemm_epi_kernel");
+}
+
+// One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
+static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
+                        cudaStream_t st) {
+  h->timer.names.clear();
+  h->last_n = n;
+  dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
+  timer_mark(h, "embed_conv1", st);
+  if (d_ascii)
+    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_bias, h->ybuf[0], n);
+  else
+    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_bias, h->ybuf[0], n);
+  if (check_launch(h, "embed_conv1_kernel")) return 1;
+  timer_mark(h, "gather0", st);
+  if (launch_gather(h, 0, 0, n, st)) return 1;
+  if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
+  if (h->conv_impl == 0) {
+    timer_mark(h, "conv2+wv0", st);
+    if (launch_conv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1), q0
+    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
+    timer_mark(h, "conv3", st);
+    if (launch_conv_tc(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
+    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
+    timer_mark(h, "wv1", st);
+    if (launch_conv_tc(h, 2, 0, n, st)) return 1;             // y3 (buf0) -> q1
+  } else {
+    timer_mark(h, "wv0(ref)", st);
+    if (launch_wv_ref(h, 0, 0, n, st)) return 1;
+    timer_mark(h, "conv2(ref)", st);
+    if (launch_conv_ref(h, 0, 0, n, st)) return 1;
+    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
+    timer_mark(h, "conv3(ref)", st);
+    if (launch_conv_ref(h, 1, 1, n, st)) return 1;
+    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
+    timer_mark(h, "wv1(ref)", st);
+    if (launch_wv_ref(h, 1, 0, n, st)) return 1;
+  }
+  timer_mark(h, "gather1", st);
+  if (launch_gather(h, 1, 0, n, st)) return 1;
+  for (int s = 0; s < 2; ++s) {
+    timer_mark(h, s ? "logits1" : "logits0", st);
+    if (launch_sgemm(h, h->mpi[s], kPatches, h->wqk[s], kPooled, h->logits, kLogitsLd, n, kPooled, kPatches, nullptr,
+                     nullptr, nullptr, 0, st)) return 1;
+    timer_mark(h, s ? "attention1" : "attention0", st);
+    attention_kernel<<<n, 128, 0, st>>>(h->logits, h->q[s], h->h0, s * kC);
+    if (check_launch(h, "attention_kernel")) return 1;
+  }
+  timer_mark(h, "head", st);
+  if (launch_sgemm(h, h->h0, 256, h->d0w, kHidden, h->h1, kHidden, n, kHidden, 256, h->d0b, h->bn0_scale, h->bn0_shift, 1, st)) return 1;
+  if (launch_sgemm(h, h->h1, kHidden, h->d1w, kHidden, h->h2, kHidden, n, kHidden, kHidden, h->d1b, h->bn1_scale, h->bn1_shift, 1, st)) return 1;
+  dense3_softmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(h->h2, h->d2w, h->d2b, d_probs, n);
+  if (check_launch(h, "dense3_softmax_kernel")) return 1;
+  timer_mark(h, "end", st);
+  return 0;
+}
+
+static int check_device_status(gnm_handle* h) {
+  if (h->status && h->status->code != kDevOk) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "device-side failure %d (mbarrier timeout) tag=%d block=%d thread=%d",
+                  h->status->code, h->status->info0, h->status->info1, h->status->info2);
+    return fail(buf);
+  }
+  return 0;
+}
+
+static int forward_any(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs, void* stream) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("negative window count");
+  if (n == 0) return 0;
+  if ((!d_ascii && !d_tok) || !d_probs) return fail("null buffer");
+  GNM_CUDA(cudaSetDevice(h->device));
+  if (check_device_status(h)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int off = 0; off < n; off += h->max_batch) {
+    const int m = std::min(h->max_batch, n - off);
+    if (forward_step(h, d_ascii ? d_ascii + static_cast<size_t>(off) * kWindow : nullptr,
+                     d_tok ? d_tok + static_cast<size_t>(off) * kTok : nullptr, m,
+                     d_probs + static_cast<size_t>(off) * 3, st)) return 1;
+  }
+  return 0;
+}
+
+extern "C" int gnm_forward_ascii(gnm_handle* h, const uint8_t* d_ascii, int n, float* d_probs, void* stream) {
+  return forward_any(h, d_ascii, nullptr, n, d_probs, stream);
+}
+extern "C" int gnm_forward_tokens(gnm_handle* h, const uint16_t* d_tokens, int n, float* d_probs, void* stream) {
+  return forward_any(h, nullptr, d_tokens, n, d_probs, stream);
+}
+
+extern "C" int gnm_encode(gnm_handle* h, const uint8_t* d_ascii, int n, uint16_t* d_tokens, void* stream) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("negative window count");
+  if (n == 0) return 0;
+  if (!d_ascii || !d_tokens) return fail("null buffer");
+  if (reinterpret_cast<uintptr_t>(d_ascii) % 16) return fail("gnm_encode: d_ascii must be 16-byte aligned");
+  GNM_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int off = 0; off < n; off += 32768) {                     // gridDim.y limit is 65535
+    const int m = std::min(32768, n - off);
+    dim3 grid((kTok + kEncSeg - 1) / kEncSeg, m);
+    encode_tokens_kernel<<<grid, kEncThreads, 0, st>>>(d_ascii + static_cast<size_t>(off) * kWindow,
+                                                      d_tokens + static_cast<size_t>(off) * kTok, m);
+    if (check_launch(h, "encode_tokens_kernel")) return 1;
+  }
+  return 0;
+}
+
+static int segment_any(gnm_handle* h, const float* d_probs, const int32_t* d_offsets, int n_contigs, float* d_out,
+                       void* stream, bool mean) {
+  if (!h) return fail("null handle");
+  if (n_contigs < 0) return fail("negative contig count");
+  if (n_contigs == 0) return 0;
+  if (!d_probs || !d_offsets || !d_out) return fail("null buffer");
+  GNM_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (n_contigs + 127) / 128;
+  if (mean) segment_reduce_kernel<true><<<grid, 128, 0, st>>>(d_probs, d_offsets, n_contigs, d_out);
+  else segment_reduce_kernel<false><<<grid, 128, 0, st>>>(d_probs, d_offsets, n_contigs, d_out);
+  return check_launch(h, "segment_reduce_kernel");
+}
+extern "C" int gnm_segment_mean(gnm_handle* h, const float* d_probs, const int32_t* d_offsets, int n_contigs,
+                                float* d_mean, void* stream) {
+  return segment_any(h, d_probs, d_offsets, n_contigs, d_mean, stream, true);
+}
+extern "C" int gnm_segment_sum(gnm_handle* h, const float* d_probs, const int32_t* d_offsets, int n_contigs,
+                               float* d_sum4, void* stream) {
+  return segment_any(h, d_probs, d_offsets, n_contigs, d_sum4, stream, false);
+}
+
+// Host buffers in, host buffers out; H2D of step i+1 overlaps compute of step i.
+extern "C" int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_probs) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("negative window count");
+  if (n == 0) return 0;
+  if (!h_ascii || !h_probs) return fail("null buffer");
+  GNM_CUDA(cudaSetDevice(h->device));
+  if (check_device_status(h)) return 1;
+  const int mb = h->max_batch;
+  const int steps = (n + mb - 1) / mb;
+  for (int i = 0; i < steps; ++i) {
+    const int b = i & 1;
+    const int off = i * mb;
+    const int m = std::min(mb, n - off);
+    if (i >= 2) GNM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->in_free[b], 0));
+    GNM_CUDA(cudaMemcpyAsync(h->in_stage[b], h_ascii + static_cast<size_t>(off) * kWindow,
+                             static_cast<size_t>(m) * kWindow, cudaMemcpyHostToDevice, h->copy_stream));
+    GNM_CUDA(cudaEventRecord(h->in_ready[b], h->copy_stream));
+    GNM_CUDA(cudaStreamWaitEvent(h->compute_stream, h->in_ready[b], 0));
+    if (forward_step(h, h->in_stage[b], nullptr, m, h->out_stage[b], h->compute_stream)) return 1;
+    GNM_CUDA(cudaEventRecord(h->in_free[b], h->compute_stream));
+    GNM_CUDA(cudaMemcpyAsync(h_probs + static_cast<size_t>(off) * 3, h->out_stage[b], static_cast<size_t>(m) * 3 * sizeof(float),
+                             cudaMemcpyDeviceToHost, h->compute_stream));
+  }
+  GNM_CUDA(cudaStreamSynchronize(h->compute_stream));
+  return check_device_status(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
+  if (!h || !name) return fail("null argument");
+  const std::string k(name);
+  if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
+  else if (k == "desc_base_mode") h->desc_base_mode = value ? 1 : 0;
+  else if (k == "debug_stop") h->debug_stop = value;
+  else if (k == "profile_stages") h->profile_stages = value ? 1 : 0;
+  else return fail("unknown option: " + k);
+  return 0;
+}
+extern "C" int gnm_get_option(gnm_handle* h, const char* name, int* value) {
+  if (!h || !name || !value) return fail("null argument");
+  const std::string k(name);
+  if (k == "conv_impl") *value = h->conv_impl;
+  else if (k == "desc_base_mode") *value = h->desc_base_mode;
+  else if (k == "debug_stop") *value = h->debug_stop;
+  else if (k == "profile_stages") *value = h->profile_stages;
+  else if (k == "max_batch") *value = h->max_batch;
+  else if (k == "num_sms") *value = h->num_sms;
+  else return fail("unknown option: " + k);
+  return 0;
+}
+extern "C" long long gnm_kernel_launches(gnm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count) {
+  if (!h || !count) return fail("null argument");
+  GNM_CUDA(cudaSetDevice(h->device));
+  const int ns = static_cast<int>(h->timer.names.size()) - 1;
+  if (ns <= 0) { *count = 0; return 0; }
+  GNM_CUDA(cudaEventSynchronize(h->timer.events[ns]));
+  const int cap = *count;
+  int k = 0;
+  for (; k < ns && k < cap; ++k) {
+    float t = 0.f;
+    GNM_CUDA(cudaEventElapsedTime(&t, h->timer.events[k], h->timer.events[k + 1]));
+    if (names) names[k] = h->timer.names[k];
+    if (ms) ms[k] = t;
+  }
+  *count = k;
+  return 0;
+}
+
+extern "C" int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d_dst, void* stream) {
+  if (!h || !which || !d_dst) return fail("null argument");
+  if (n < 1 || n > h->max_batch) return fail("gnm_debug_fetch: n out of range");
+  GNM_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const std::string k(which);
+  const float* src = nullptr;
+  size_t count = 0;
+  if (k == "buf0" || k == "buf1") {
+    const size_t rows = static_cast<size_t>(n) * kTok;
+    join_rows_kernel<<<static_cast<unsigned>((rows * kC + 255) / 256), 256, 0, st>>>(h->ybuf[k == "buf1"], d_dst, rows);
+    return check_launch(h, "join_rows_kernel");
+  } else if (k == "q0" || k == "q1") { src = h->q[k == "q1"]; count = static_cast<size_t>(n) * kPooled * kC; }
+  else if (k == "mpi0" || k == "mpi1") { src = h->mpi[k == "mpi1"]; count = static_cast<size_t>(n) * kPatches; }
+  else if (k == "h0") { src = h->h0; count = static_cast<size_t>(n) * 256; }
+  else if (k == "logits") { src = h->logits; count = static_cast<size_t>(n) * kLogitsLd; }
+  else return fail("gnm_debug_fetch: unknown buffer " + k);
+  GNM_CUDA(cudaMemcpyAsync(d_dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}

@@ -1,0 +1,151 @@
+// K5 (attention logits GEMM), K7 (dense head) and K8 (per-contig segment reduction).
+//
+// Reference semantics:
+//   alpha logits = mpi @ w_qk                      genomad/neural_network/igloo.py:211
+//   Dense(512)+BatchNormalization+relu             genomad/neural_network/model.py:28-30, 40-42
+//         keras BN inference: x * inv + (beta - mean * inv), inv = gamma * rsqrt(var + 1e-3)
+//   Dense(3, softmax)                              genomad/neural_network/model.py:44
+//   tf.math.segment_mean(preds, contig_ids)        genomad/modules/nn_classification.py:320
+#pragma once
+#include "common.cuh"
+
+namespace gnm {
+
+// ------------------------------------------------------------------------------------------
+// C[M][ldc] = epi(A[M][K] @ B[K][N]) in fp32 on the CUDA cores (these GEMMs are < 0.3 % of the
+// model's FLOPs).  64x64 tile, 16-deep K slices, 256 threads x (4x4) outputs, guards on every edge.
+// epi: v = acc + bias[n]; if scale: v = v * scale[n] + shift[n]; if relu: v = max(v, 0).
+// ------------------------------------------------------------------------------------------
+constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
+
+__global__ void __launch_bounds__(kGemmThreads)
+sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                 float* __restrict__ C, int ldc, int M, int N, int K,
+                 const float* __restrict__ bias, const float* __restrict__ scale,
+                 const float* __restrict__ shift, int relu) {
+  __shared__ float s_a[kGemmBK][kGemmBM + 4];
+  __shared__ float s_b[kGemmBK][kGemmBN + 4];
+  const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+    // A tile: 64 rows x 16 k  (thread -> row = tid/4, 4 consecutive k)
+    {
+      const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) * 4;
+      const int gm = m0 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gk = k0 + kk + i;
+        s_a[kk + i][r] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
+      }
+    }
+    // B tile: 16 k x 64 cols (thread -> k = tid/16, 4 consecutive cols)
+    {
+      const int kk = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
+      const int gk = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gn = n0 + c + i;
+        s_b[kk][c + i] = (gk < K && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGemmBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = s_a[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = s_b[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (scale) v = v * scale[gn] + shift[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      C[static_cast<size_t>(gm) * ldc + gn] = v;
+    }
+  }
+}
+
+// Dense(512 -> 3) + softmax: one warp per window.
+__global__ void __launch_bounds__(256)
+dense3_softmax_kernel(const float* __restrict__ h2,    // [n][512]
+                      const float* __restrict__ Wd,    // [512][3]
+                      const float* __restrict__ bd,    // [3]
+                      float* __restrict__ probs,       // [n][3]
+                      int n) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float* x = h2 + static_cast<size_t>(w) * kHidden;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = lane; k < kHidden; k += 32) {
+    const float v = x[k];
+    a0 = fmaf(v, Wd[k * 3 + 0], a0);
+    a1 = fmaf(v, Wd[k * 3 + 1], a1);
+    a2 = fmaf(v, Wd[k * 3 + 2], a2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+  }
+  if (lane == 0) {
+    a0 += bd[0]; a1 += bd[1]; a2 += bd[2];
+    const float m = fmaxf(a0, fmaxf(a1, a2));
+    const float e0 = expf(a0 - m), e1 = expf(a1 - m), e2 = expf(a2 - m);
+    const float inv = 1.f / (e0 + e1 + e2);
+    probs[static_cast<size_t>(w) * 3 + 0] = e0 * inv;
+    probs[static_cast<size_t>(w) * 3 + 1] = e1 * inv;
+    probs[static_cast<size_t>(w) * 3 + 2] = e2 * inv;
+  }
+}
+
+// Per-contig reduction: one thread per contig walks its window range in order (fp32 running sum,
+// the order tf.math.segment_mean's CPU kernel uses), so the result does not depend on the launch shape.
+template <bool kMean>
+__global__ void segment_reduce_kernel(const float* __restrict__ probs, const int32_t* __restrict__ offsets,
+                                      int n_contigs, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contigs) return;
+  const int b = offsets[c], e = offsets[c + 1];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = b; i < e; ++i) {
+    s0 += probs[static_cast<size_t>(i) * 3 + 0];
+    s1 += probs[static_cast<size_t>(i) * 3 + 1];
+    s2 += probs[static_cast<size_t>(i) * 3 + 2];
+  }
+  const float cnt = static_cast<float>(e - b);
+  if (kMean) {
+    const float d = cnt > 0.f ? cnt : 1.f;
+    out[static_cast<size_t>(c) * 3 + 0] = s0 / d;
+    out[static_cast<size_t>(c) * 3 + 1] = s1 / d;
+    out[static_cast<size_t>(c) * 3 + 2] = s2 / d;
+  } else {
+    out[static_cast<size_t>(c) * 4 + 0] = s0;
+    out[static_cast<size_t>(c) * 4 + 1] = s1;
+    out[static_cast<size_t>(c) * 4 + 2] = s2;
+    out[static_cast<size_t>(c) * 4 + 3] = cnt;
+  }
+}
+
+}  // namespace gnm

@@ -1,0 +1,137 @@
+// K0: ASCII -> 4-mer tokens, and K0+K1 fused: ASCII/tokens -> first conv layer output.
+//
+// Reference semantics:
+//   tokenize_dna            genomad/sequence.py:170-193  (closed form: tok = 0 if any of the 4 bytes
+//                           is not one of 'A','C','G','T' (65,67,71,84), else 1 + base-4 value)
+//   one-hot + Conv1D#1      genomad/neural_network/model.py:11, igloo.py:45-48
+//                           y1[t] = lrelu(b + sum_{j=0..5, t-5+j>=0} W1[j][tok[t-5+j]][:])
+//                           (causal zero padding adds nothing -- it is NOT token 0)
+#pragma once
+#include "common.cuh"
+
+namespace gnm {
+
+// 2-bit code of an upper-case nucleotide byte, or 4 for anything else
+__device__ __forceinline__ uint32_t base_code(uint8_t b) {
+  return b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : 4u;
+}
+__device__ __forceinline__ uint16_t kmer_token(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+  const uint32_t bad = (c0 | c1 | c2 | c3) & 4u;
+  const uint32_t v = 1u + 64u * c0 + 16u * c1 + 4u * c2 + c3;
+  return bad ? uint16_t(0) : uint16_t(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// K0 (stand-alone): one CTA per (window, 2048-token segment).  Bytes are staged through shared
+// memory with 16-byte coalesced loads; every thread then emits 8 consecutive tokens as one
+// 16-byte store.  Pure byte/integer work, HBM-bound: 6000 B in + 11994 B out per window.
+// ------------------------------------------------------------------------------------------
+constexpr int kEncSeg = 2048;                         // tokens per CTA
+constexpr int kEncThreads = kEncSeg / 8;              // 256
+
+__global__ void __launch_bounds__(kEncThreads)
+encode_tokens_kernel(const uint8_t* __restrict__ ascii, uint16_t* __restrict__ tokens, int n_windows) {
+  __shared__ __align__(16) uint8_t s_b[kEncSeg + 16];
+  const int w = blockIdx.y;
+  const int t0 = blockIdx.x * kEncSeg;
+  const uint8_t* src = ascii + static_cast<size_t>(w) * kWindow;
+  // window rows are 6000 B apart: 16-byte aligned (6000 = 375 * 16) as long as the base is.
+  for (int i = threadIdx.x; i < (kEncSeg + 16) / 16; i += blockDim.x) {
+    const int off = t0 + i * 16;
+    uint4 v = make_uint4(0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu);   // 'N'
+    if (off + 16 <= kWindow) {
+      v = *reinterpret_cast<const uint4*>(src + off);
+    } else if (off < kWindow) {
+      uint8_t tmp[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tmp[k] = (off + k < kWindow) ? src[off + k] : uint8_t('N');
+      v = *reinterpret_cast<uint4*>(tmp);
+    }
+    *reinterpret_cast<uint4*>(s_b + i * 16) = v;
+  }
+  __syncthreads();
+  const int lt = threadIdx.x * 8;            // first token (within the segment) of this thread
+  uint32_t c[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) c[k] = base_code(s_b[lt + k]);
+  uint16_t out[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = kmer_token(c[k], c[k + 1], c[k + 2], c[k + 3]);
+  uint16_t* dst = tokens + static_cast<size_t>(w) * kTok;
+  const int t = t0 + lt;
+  // token rows are 5997*2 B apart -> not 16-byte aligned in general: scalar stores
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (t + k < kTok) dst[t + k] = out[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// K0+K1 fused: one CTA per (window, 256-position segment).  Tokens are computed into shared
+// memory (from ASCII, or copied from a token buffer), then one warp per position sums the six
+// 512-byte rows of the [6][257][128] table (L2-resident, 789 KB), adds the bias, applies
+// LeakyReLU and writes the activation row as fp16 hi | fp16 lo (256 halves = 512 B).
+// Taps are added in the fixed order j = 0..5 so results do not depend on scheduling.
+// ------------------------------------------------------------------------------------------
+constexpr int kEmbSeg = 256;
+constexpr int kEmbThreads = 256;
+
+template <bool kFromAscii>
+__global__ void __launch_bounds__(kEmbThreads)
+embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict__ tokens_in,
+                   const float* __restrict__ table,   // [6][257][128]
+                   const float* __restrict__ bias,    // [128]
+                   __half* __restrict__ y_out,        // [n][5997][256]
+                   int n_windows) {
+  __shared__ int16_t s_tok[kEmbSeg + 8];    // s_tok[i] = token at position t0 - 5 + i, or -1 (causal pad)
+  __shared__ uint8_t s_b[kEmbSeg + 16];
+  const int w = blockIdx.y;
+  const int t0 = blockIdx.x * kEmbSeg;
+  if (kFromAscii) {
+    const uint8_t* src = ascii + static_cast<size_t>(w) * kWindow;
+    for (int i = threadIdx.x; i < kEmbSeg + 8 + 3; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      s_b[i] = (p >= 0 && p < kWindow) ? src[p] : uint8_t('N');
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kEmbSeg + 5; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      int16_t tk = -1;
+      if (p >= 0 && p < kTok)
+        tk = static_cast<int16_t>(kmer_token(base_code(s_b[i]), base_code(s_b[i + 1]),
+                                             base_code(s_b[i + 2]), base_code(s_b[i + 3])));
+      s_tok[i] = tk;
+    }
+  } else {
+    const uint16_t* src = tokens_in + static_cast<size_t>(w) * kTok;
+    for (int i = threadIdx.x; i < kEmbSeg + 5; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      s_tok[i] = (p >= 0 && p < kTok) ? static_cast<int16_t>(src[p]) : int16_t(-1);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 b4 = reinterpret_cast<const float4*>(bias)[lane];
+  const float4* tab4 = reinterpret_cast<const float4*>(table);
+  for (int i = warp; i < kEmbSeg; i += kEmbThreads / 32) {
+    const int t = t0 + i;
+    if (t >= kTok) break;
+    float4 v[kTaps];
+#pragma unroll
+    for (int j = 0; j < kTaps; ++j) {
+      const int tk = s_tok[i + j];                   // position t - 5 + j
+      v[j] = tk >= 0 ? __ldg(tab4 + (static_cast<size_t>(j) * kVocab + tk) * (kC / 4) + lane)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float4 a = v[0];
+#pragma unroll
+    for (int j = 1; j < kTaps; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    a.x = lrelu(a.x + b4.x); a.y = lrelu(a.y + b4.y); a.z = lrelu(a.z + b4.z); a.w = lrelu(a.w + b4.w);
+    __half h0, h1, h2, h3, l0, l1, l2, l3;
+    split_f16(a.x, h0, l0); split_f16(a.y, h1, l1); split_f16(a.z, h2, l2); split_f16(a.w, h3, l3);
+    __half* row = y_out + (static_cast<size_t>(w) * kTok + t) * kRowHalfs;
+    *reinterpret_cast<uint2*>(row + lane * 4) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+    *reinterpret_cast<uint2*>(row + kC + lane * 4) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+  }
+}
+
+}  // namespace gnm

@@ -1,0 +1,152 @@
+/*
+ * gnm.h -- C ABI of libgnm.so: the B200 (sm_100a) implementation of geNomad's
+ * nn-classification hot path.
+ *
+ * The reference has no FFI: its hot path is Python calling TensorFlow/Keras and numba
+ * (reference genomad/modules/nn_classification.py, genomad/neural_network/{model,igloo}.py,
+ * genomad/sequence.py).  Each entry point below replaces one reference call site; the
+ * ctypes binding a geNomad maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; gnm_last_error() returns a
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - pointers prefixed d_ are DEVICE pointers on the handle's device, h_ are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise; the caller owns all
+ *     input/output buffers and the stream.
+ *   - one handle per (device, stream user); calls on one handle are not thread-safe.
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef GNM_H_
+#define GNM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNM_WINDOW 6000   /* nucleotides per window     (nn_classification.py:68)  */
+#define GNM_TOKENS 5997   /* 4-mer tokens per window    (sequence.py:172; model.py:15) */
+#define GNM_CLASSES 3     /* chromosome, plasmid, virus (model.py:44) */
+
+typedef struct gnm_handle gnm_handle;
+
+/* One IGLOO1D_kernel's weights, Keras layouts (reference igloo.py:117-188). */
+typedef struct gnm_igloo_weights {
+  const float*   w_mult;    /* [1][2100][4][128] */
+  const float*   w_summer;  /* [1][512][1]       */
+  const float*   w_bias;    /* [1][2100]         */
+  const float*   w_qk;      /* [2100][749]       */
+  const float*   w_v;       /* [1][128][128]     */
+  const int32_t* patches;   /* [2100][4][1], values in [0, 5997) */
+} gnm_igloo_weights;
+
+typedef struct gnm_bn_weights {   /* keras BatchNormalization, epsilon = 1e-3 */
+  const float* gamma; const float* beta; const float* moving_mean; const float* moving_variance;  /* [512] each */
+} gnm_bn_weights;
+
+/*
+ * All weights of create_classifier() (reference model.py:34-45) as HOST pointers in the exact
+ * layouts stored in genomad/data/nn_classifier.h5 (Keras: Conv1D kernel [k][in][out], Dense
+ * kernel [in][out]).  Replaces nn_model.load_weights(...) (nn_classification.py:310).
+ */
+typedef struct gnm_weights {
+  const float* conv1_kernel;  /* [6][257][128]  /model/conv1d   */
+  const float* conv1_bias;    /* [128] */
+  const float* conv2_kernel;  /* [6][128][128]  /model/conv1d_1 */
+  const float* conv2_bias;
+  const float* conv3_kernel;  /* [6][128][128]  /model/conv1d_2 */
+  const float* conv3_bias;
+  gnm_igloo_weights igloo[2]; /* [0] on conv1 output, [1] on conv3 output (igloo.py:54-82) */
+  const float* dense0_kernel; /* [256][512]  /model/dense */
+  const float* dense0_bias;   /* [512] */
+  gnm_bn_weights bn0;         /* /model/batch_normalization */
+  const float* dense1_kernel; /* [512][512]  /dense_1 */
+  const float* dense1_bias;
+  gnm_bn_weights bn1;         /* /batch_normalization_1 */
+  const float* dense2_kernel; /* [512][3]    /dense_2 */
+  const float* dense2_bias;   /* [3] */
+} gnm_weights;
+
+/* Thread-local description of the last failure on the calling thread. */
+const char* gnm_last_error(void);
+
+/* Library / build information, e.g. "libgnm 0.1 sm_100a". */
+const char* gnm_version(void);
+
+/*
+ * Create a classifier on CUDA device `device`.  Copies and re-packs the weights (fp16 hi/lo
+ * operand splits, folded patch weights, batch-norm scale/shift) and allocates a workspace able
+ * to process `max_batch` windows per internal step.  Synchronous.
+ * Replaces create_classifier() + load_weights() (nn_classification.py:309-310).
+ */
+int gnm_create(int device, const gnm_weights* weights, int max_batch, gnm_handle** out);
+int gnm_destroy(gnm_handle* h);
+
+/*
+ * ASCII windows -> 4-mer tokens.  d_ascii: uint8 [n][6000] (upper-cased, N-padded by the caller,
+ * as nn_classification.py:72 does); d_tokens: uint16 [n][5997], 0 = k-mer containing a non-ACGT
+ * byte, else 1 + base-4 value.  Bit-exact replacement of sequence.tokenize_dna(seq, 4)
+ * (sequence.py:170-193).
+ */
+int gnm_encode(gnm_handle* h, const uint8_t* d_ascii, int n, uint16_t* d_tokens, void* stream);
+
+/*
+ * Per-window class probabilities from ASCII windows (encode fused with the first layer).
+ * d_probs: float [n][3] (chromosome, plasmid, virus).  Replaces the TFRecord round trip +
+ * nn_model.predict(batch) (nn_classification.py:73,316-317).  n may exceed max_batch (processed
+ * in steps).
+ */
+int gnm_forward_ascii(gnm_handle* h, const uint8_t* d_ascii, int n, float* d_probs, void* stream);
+
+/* Same, from tokens (uint16 [n][5997], values 0..256): nn_model.predict on an int64[B,5997] batch. */
+int gnm_forward_tokens(gnm_handle* h, const uint16_t* d_tokens, int n, float* d_probs, void* stream);
+
+/*
+ * Per-contig reduction of window probabilities.  d_offsets: int32 [n_contigs + 1], window range
+ * of contig c is [offsets[c], offsets[c+1]) (contig ids are sorted, nn_classification.py:66-75).
+ * gnm_segment_mean replaces tf.math.segment_mean (nn_classification.py:320): fp32 running sum in
+ * window order, divided by the count; empty segments give zeros.
+ * gnm_segment_sum writes float [n_contigs][4] = (sum p0, sum p1, sum p2, count) -- the partial
+ * a rank contributes when a contig's windows span several GPUs.
+ */
+int gnm_segment_mean(gnm_handle* h, const float* d_probs, const int32_t* d_offsets, int n_contigs,
+                     float* d_mean, void* stream);
+int gnm_segment_sum(gnm_handle* h, const float* d_probs, const int32_t* d_offsets, int n_contigs,
+                    float* d_sum4, void* stream);
+
+/*
+ * Host-buffer convenience path (what a drop-in module calls): h_ascii uint8 [n][6000] in host
+ * memory (pinned or pageable) -> h_probs float [n][3].  Copies in steps of max_batch on two
+ * internal streams so the copy of step i+1 overlaps the compute of step i.  Synchronous.
+ */
+int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_probs);
+
+/* ---- introspection / test hooks (not needed by a drop-in caller) ------------------------- */
+
+/* Options: "conv_impl" 0 = tcgen05 tensor-core path (default), 1 = fp32 CUDA-core validation
+ * kernels; "desc_base_mode" 0/1 = UMMA descriptor base-offset policy for shifted rows. */
+int gnm_set_option(gnm_handle* h, const char* name, int value);
+int gnm_get_option(gnm_handle* h, const char* name, int* value);
+
+/* Number of kernels this library has launched through handle h (monotonic). */
+long long gnm_kernel_launches(gnm_handle* h);
+
+/* Per-stage device time of the most recent gnm_forward_* step, in milliseconds (CUDA events;
+ * requires option "profile_stages" = 1, which serialises the step).  names/ms arrays of length
+ * >= *count on input; *count on output = number of stages written. */
+int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count);
+
+/*
+ * Copy an intermediate of the most recent forward step (first min(n, max_batch) windows) to a
+ * device buffer as fp32.  which: "y1","y2","y3" [n][5997][128]; "q0","q1" [n][749][128];
+ * "mpi0","mpi1" [n][2100]; "h0" [n][256].  Used by the per-kernel parity tests.
+ */
+int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNM_H_ */
