@@ -1,0 +1,50 @@
+"""
+Command line of the nn-classification module -- same arguments and options as
+``genomad nn-classification`` (reference genomad/cli.py:714-774).  rich-click is not a dependency;
+plain click gives the same option surface.
+
+    python -m genomad_b200.cli nn-classification [OPTIONS] INPUT OUTPUT
+    torchrun --nproc-per-node 8 -m genomad_b200.cli nn-classification INPUT OUTPUT     # 8 GPUs
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import click
+
+from . import __version__
+from .utils import get_n_available_cpus
+
+CONTEXT_SETTINGS = dict(help_option_names=["-h", "--help"])
+
+
+@click.group(context_settings=CONTEXT_SETTINGS)
+@click.version_option(version=__version__, prog_name="geNomad-B200")
+def cli():
+    """geNomad nn-classification on NVIDIA B200."""
+
+
+@cli.command(name="nn-classification", context_settings=CONTEXT_SETTINGS)
+@click.argument("input", type=click.Path(path_type=Path, exists=True))
+@click.argument("output", type=click.Path(path_type=Path))
+@click.option("--restart", is_flag=True, default=False, show_default=True,
+              help="Overwrite existing intermediate files.")
+@click.option("--threads", "-t", type=int, default=get_n_available_cpus(), show_default=True,
+              help="Number of threads to use.")
+@click.option("--verbose/--quiet", "-v/-q", is_flag=True, default=True, show_default=True,
+              help="Display the execution log.")
+@click.option("--cleanup", is_flag=True, default=False, show_default=True,
+              help="Delete intermediate files after execution.")
+@click.option("--single-window", is_flag=True, default=False, show_default=True,
+              help="Use only the first window (6,000 bases) of each sequence to perform the classification.")
+@click.option("--batch-size", type=int, default=128, show_default=True,
+              help="Number of data points per batch of prediction.")
+def nn_classification(input, output, single_window, batch_size, restart, threads, verbose, cleanup):
+    """Classify the sequences in the INPUT file (FASTA format) using the geNomad neural network and write
+    the results to the OUTPUT directory."""
+    from . import nn_classification as module
+    module.main(input, output, single_window, batch_size, restart, threads, verbose, cleanup)
+
+
+if __name__ == "__main__":
+    cli()

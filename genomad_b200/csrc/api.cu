@@ -48,7 +48,6 @@ struct gnm_handle {
   long long launches = 0;
   // options
   int conv_impl = 0;        // 0 tcgen05, 1 fp32 validation kernels
-  int desc_base_mode = 0;
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   // weights on device
@@ -152,7 +151,7 @@ static void pack_matrix_stages(std::vector<__half>& dst, const float* Wkn) {   /
 // ------------------------------------------------------------------------------------------------
 extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_handle** out) {
   if (!w || !out) return fail("gnm_create: null argument");
-  if (max_batch < 1) return fail("gnm_create: max_batch must be >= 1");
+  if (max_batch < 1 || max_batch > 32768) return fail("gnm_create: max_batch must be in [1, 32768]");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("gnm_create: no CUDA device available (libgnm has no CPU fallback)");
@@ -311,7 +310,6 @@ static void timer_mark(gnm_handle* h, const char* name, cudaStream_t st) {
 static int launch_conv_tc(gnm_handle* h, int which, int in_buf, int n, cudaStream_t st) {
   ConvTcParams p;
   p.n_tiles = n * kTilesPerWin;
-  p.desc_base_mode = h->desc_base_mode;
   p.status = h->status;
   const int grid = std::min(h->num_sms, p.n_tiles);
   if (which == 0) {          // conv2: y[in] -> y[1-in], q0 from the input
@@ -534,7 +532,6 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (!h || !name) return fail("null argument");
   const std::string k(name);
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
-  else if (k == "desc_base_mode") h->desc_base_mode = value ? 1 : 0;
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "profile_stages") h->profile_stages = value ? 1 : 0;
   else return fail("unknown option: " + k);
@@ -544,7 +541,6 @@ extern "C" int gnm_get_option(gnm_handle* h, const char* name, int* value) {
   if (!h || !name || !value) return fail("null argument");
   const std::string k(name);
   if (k == "conv_impl") *value = h->conv_impl;
-  else if (k == "desc_base_mode") *value = h->desc_base_mode;
   else if (k == "debug_stop") *value = h->debug_stop;
   else if (k == "profile_stages") *value = h->profile_stages;
   else if (k == "max_batch") *value = h->max_batch;

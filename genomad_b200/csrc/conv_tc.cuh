@@ -19,6 +19,9 @@
 // slab of a tile into shared memory ONCE (SWIZZLE_128B); tap j is the same slab read 'j' rows further
 // down, i.e. only the UMMA descriptor start address changes (row j of the slab is position t0-5+j,
 // and TMA zero-fills rows with t < 0 or t >= 5997, which is exactly Keras' causal padding).
+// Measured on B200 (profiles/r01_bringup.md): the 128B swizzle is a function of the absolute shared-
+// memory address, so a descriptor whose start address is 'j' rows (j*128 B) into a 1024B-aligned
+// slab reads the rows TMA wrote, with descriptor base_offset = 0 -- no per-tap reload is needed.
 // Weights stream through a 4-stage ring of 16 KB stages (one K-half of one [128 out][128 in] fp16
 // matrix, K-major), re-packed on the host in consumption order.
 //
@@ -49,7 +52,6 @@ struct ConvTcParams {
   __half* y_out;            // [n][5997][256] or nullptr
   float* q_out;             // [n][749][128] or nullptr
   int n_tiles;              // n_windows * 47
-  int desc_base_mode;       // 0: base_offset = 0; 1: base_offset = (addr >> 7) & 7
   DeviceStatus* status;
 };
 
@@ -149,13 +151,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         const uint32_t a_lo = a_base + (2 + kh) * kARegion + arow * 128;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bdesc = umma_desc_sw128(b_addr + kk * 32, 0);
+          const uint64_t bdesc = umma_desc_sw128(b_addr + kk * 32);
           const uint32_t ah = a_hi + kk * 32;
-          umma_f16(acc, umma_desc_sw128(ah, p.desc_base_mode ? (ah >> 7) : 0), bdesc, kIdesc,
+          umma_f16(acc, umma_desc_sw128(ah), bdesc, kIdesc,
                    (first && kk == 0) ? 0u : 1u);
           if (!w_lo) {
             const uint32_t al = a_lo + kk * 32;
-            umma_f16(acc, umma_desc_sw128(al, p.desc_base_mode ? (al >> 7) : 0), bdesc, kIdesc, 1u);
+            umma_f16(acc, umma_desc_sw128(al), bdesc, kIdesc, 1u);
           }
         }
         umma_commit(&b_empty[s]);          // stage is free once these MMAs have read it

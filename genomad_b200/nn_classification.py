@@ -1,0 +1,184 @@
+"""
+``nn-classification`` module driver -- drop-in for ``genomad.nn_classification.main``
+(reference genomad/modules/nn_classification.py:21-427): same signature, same files on disk
+(<prefix>_nn_classification.{log,json,tsv,npz}, <prefix>_encoded_sequences/, the provirus twins), same
+skip/restart/cleanup semantics, same error behaviour (message + sys.exit(1)).
+
+What changed underneath: the FASTA is turned into one dense uint8 window matrix on the host
+(genomad_b200.sequence), shipped to the B200 in steps of ``batch_size`` windows, tokenised and
+classified by libgnm.so (hand-written sm_100a kernels), and reduced per contig on the device.
+TensorFlow, TFRecords and the per-batch ``predict`` call are gone.  With torchrun (WORLD_SIZE > 1)
+windows are sharded across GPUs and combined over NCCL (genomad_b200.dist); rank 0 writes the outputs.
+"""
+from __future__ import annotations
+
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from . import __version__, dist as gdist, sequence, utils
+from ._paths import NNOutputs
+
+_HEADER = "seq_name\tchromosome_score\tplasmid_score\tvirus_score\n"
+
+
+def _make_classifier(batch_size: int, device: int):
+    """Factory (patched in CPU tests): the real one needs a B200 and libgnm.so -- no fallback."""
+    from .engine import Classifier
+    return Classifier(None, device=device, max_batch=max(1, int(batch_size)))
+
+
+def _classify_windows(clf, windows: np.ndarray, offsets: np.ndarray, info: gdist.DistInfo,
+                      contig_reduce: str = "gather") -> np.ndarray:
+    """windows uint8 [W,6000] + contig offsets -> float32 [n_contigs,3] per-contig mean (identical on all ranks)."""
+    import torch
+    n = windows.shape[0]
+    start, end = gdist.shard_bounds(n, info.world_size, info.rank)
+    local = clf.classify_host(windows[start:end])                              # [W_local, 3] float32 (host)
+    dev = torch.device("cuda", clf.device)
+    local_t = torch.from_numpy(local).to(dev)
+    if contig_reduce == "allreduce" and info.world_size > 1:
+        loc_off = torch.from_numpy(gdist.local_offsets(offsets, start, end)).to(dev)
+        partials = clf.segment_sum(local_t, loc_off)
+        partials = gdist.allreduce_partials(partials, info.world_size)
+        return gdist.finish_mean(partials).cpu().numpy()
+    probs = gdist.gather_window_probs(local_t, n, info.world_size)
+    off_t = torch.from_numpy(offsets.astype(np.int32)).to(dev)
+    return clf.segment_mean(probs, off_t).cpu().numpy()
+
+
+def _write_tsv(path: Path, names, preds) -> None:
+    with open(path, "w") as fout:
+        fout.write(_HEADER)
+        for name, s in zip(names, preds):
+            fout.write(f"{name}\t{float(s[0]):.4f}\t{float(s[1]):.4f}\t{float(s[2]):.4f}\n")
+
+
+def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_window, names_key, ids_key, what, is_main):
+    if enc_dir.is_dir() and is_main:
+        shutil.rmtree(enc_dir)
+    console.log(f"Creating the {enc_dir} directory.")
+    if is_main:
+        enc_dir.mkdir()
+    enc = sequence.encode_fasta(fasta_path, single_window)
+    if is_main:
+        np.savez_compressed(id_path, **{names_key: enc.names, ids_key: enc.contig_ids})
+        np.save(enc_dir / f"{len(enc.contig_ids)}.windows.npy", enc.windows)
+    console.log(f"Encoded {what} data written to {enc_dir.name}.")
+    return enc
+
+
+def _load_encoded(enc_dir: Path, id_path: Path, names_key, ids_key):
+    z = np.load(id_path)
+    names, ids = z[names_key], z[ids_key]
+    files = sorted(enc_dir.glob("*.windows.npy"))
+    windows = np.load(files[0])
+    counts = np.bincount(ids, minlength=len(names)) if len(ids) else np.zeros(len(names), np.int64)
+    offsets = np.zeros(len(names) + 1, np.int32)
+    np.cumsum(counts, out=offsets[1:])
+    return sequence.EncodedFasta(names, ids, offsets, windows)
+
+
+def main(input_path, output_path, single_window, batch_size, restart, threads, verbose, cleanup):
+    input_path, output_path = Path(input_path), Path(output_path)
+    info = gdist.init_process_group_if_needed()
+    is_main = info.is_main
+    if not output_path.is_dir() and is_main:
+        output_path.mkdir()
+    prefix = input_path.stem
+    if sequence.is_compressed(input_path) != sequence.Compression.uncompressed:
+        prefix = prefix.rsplit(".", 1)[0]
+    outputs = NNOutputs(prefix, output_path)
+    console = utils.HybridConsole(output_file=outputs.nn_classification_log if is_main else None,
+                                  verbose=verbose and is_main)
+    parameter_dict = {"single_window": single_window}
+    classify_proviruses = utils.check_provirus_execution(prefix, input_path, output_path)
+
+    files = [outputs.nn_classification_execution_info, outputs.encoded_sequences_dir,
+             outputs.nn_classification_output, outputs.nn_classification_npz_output]
+    descr = ["execution parameters", "directory containing encoded sequence data",
+             "contig classification: tabular format", "contig classification: binary format"]
+    if classify_proviruses:
+        files += [outputs.encoded_proviruses_dir, outputs.provirus_nn_classification_output,
+                  outputs.provirus_nn_classification_npz_output]
+        descr += ["directory containing encoded sequence data", "provirus classification: tabular format",
+                  "provirus classification: binary format"]
+    utils.display_header(console, __version__, "nn-classification",
+                         "This will classify the input sequences into chromosome, plasmid, or virus based on the "
+                         "nucleotide sequence.", outputs.nn_classification_dir, files, descr)
+
+    if not sequence.check_fasta(input_path):
+        console.error(f"{input_path} is either empty or contains multiple entries with the same identifier. "
+                      "Please check your input FASTA file and execute genomad nn-classification again.")
+        sys.exit(1)
+    console.log("Executing genomad nn-classification.")
+
+    skip = False
+    if outputs.nn_classification_execution_info.exists() and any(p.exists() for p in files) and not restart:
+        if utils.compare_executions(input_path, parameter_dict, outputs.nn_classification_execution_info):
+            skip = True
+            console.log("Previous execution detected. Steps will be skipped unless their outputs are not found. "
+                        "Use the --restart option to force the execution of all the steps again.")
+        else:
+            console.log("The input file or the parameters changed since the last execution. "
+                        "Previous outputs will be overwritten.")
+    if not outputs.nn_classification_dir.is_dir():
+        console.log(f"Creating the {outputs.nn_classification_dir} directory.")
+        if is_main:
+            outputs.nn_classification_dir.mkdir()
+    if is_main:
+        utils.write_execution_info("nn_classification", input_path, parameter_dict,
+                                   outputs.nn_classification_execution_info)
+
+    clf = None
+
+    def classifier():
+        nonlocal clf
+        if clf is None:
+            clf = _make_classifier(batch_size, info.local_rank)
+        return clf
+
+    jobs = [("sequence", "contig", input_path, outputs.encoded_sequences_dir, outputs.seq_window_id_output,
+             "contig_names", "contig_ids", outputs.nn_classification_npz_output, outputs.nn_classification_output, True)]
+    if classify_proviruses:
+        jobs.append(("provirus", "provirus", outputs.find_proviruses_nucleotide_output, outputs.encoded_proviruses_dir,
+                     outputs.provirus_window_id_output, "provirus_names", "provirus_ids",
+                     outputs.provirus_nn_classification_npz_output, outputs.provirus_nn_classification_output, False))
+
+    for what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows in jobs:
+        # ---- encode
+        enc = None
+        if skip and id_path.exists() and len(list(enc_dir.glob("*.windows.npy"))):
+            console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
+            if not (skip and npz_path.exists()):
+                enc = _load_encoded(enc_dir, id_path, names_key, ids_key)
+        else:
+            enc = _encode_stage(console, fasta, enc_dir, id_path, single_window, names_key, ids_key, what, is_main)
+        # ---- classify
+        if skip and npz_path.exists():
+            console.log(f"{npz_path.name} was found. Skipping {what} classification.")
+            z = np.load(npz_path)
+            names, preds = z[names_key], z["predictions"]
+        else:
+            if enc.windows.shape[0] == 0:
+                if must_have_windows:
+                    console.error("No sequences were found. Please check your input FASTA.")
+                    sys.exit(1)
+                names, preds = enc.names, np.zeros((len(enc.names), 3), np.float32)
+            else:
+                preds = _classify_windows(classifier(), enc.windows, enc.offsets, info)
+                names = enc.names
+            console.log(f"{'Sequences' if what == 'sequence' else 'Proviruses'} classified.")
+            if is_main:
+                np.savez_compressed(npz_path, **{names_key: names, "predictions": preds.astype(np.float32)})
+            console.log(f"{noun.capitalize()} classification in binary format written to {npz_path.name}.")
+        if cleanup and enc_dir.is_dir() and is_main:
+            console.log(f"Deleting encoded {what} data.")
+            shutil.rmtree(enc_dir)
+        if is_main:
+            _write_tsv(tsv_path, names, preds)
+        console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
+
+    console.log("geNomad nn-classification finished!")

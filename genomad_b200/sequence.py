@@ -1,0 +1,163 @@
+"""
+Host-side FASTA reading, windowing and window-matrix construction for nn-classification.
+
+Mirrors the behaviour (not the code) of the reference's ``genomad/sequence.py:96-167`` and the
+window rules of ``genomad/modules/nn_classification.py:65-72``; the quirks that are pinned by golden
+vectors made with the real reference code (tests/golden/encoder_golden.json):
+
+  * files are read in text mode with universal newlines: ``\\r\\n`` and ``\\r`` end a line like ``\\n``;
+  * everything before the first line that starts with ``>`` is ignored;
+  * a record's name is the first whitespace-delimited token of its header line;
+  * leading/trailing ``n``/``N`` of the whole contig are stripped; records that are then empty are dropped;
+  * windows are consecutive 6000-nt slices; the last slice is kept only if it has >= 2500 nt, except
+    that the first window is always kept; ``--single-window`` keeps only the first;
+  * a window other than the first is skipped if it contains more than 4000 upper-case ``N`` in the
+    RAW text (lower-case ``n`` does not count) -- nn_classification.py:70-71;
+  * windows are upper-cased and right-padded with ``N`` to 6000 bytes (nn_classification.py:72).
+
+Unlike the reference (a Python generator of ``Sequence`` objects feeding a per-window numba call), this
+works on bytes with C-speed primitives and emits one dense uint8 matrix [n_windows, 6000] that is
+shipped to the GPU as is -- tokenisation happens on the device (csrc/encode.cuh).
+"""
+from __future__ import annotations
+
+import bz2
+import gzip
+import lzma
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Iterator, List, Optional, Tuple
+
+import numpy as np
+
+WINDOW = 6000
+MIN_TAIL = 2500
+MAX_N = 4000
+
+
+class Compression:
+    bzip2, gzip, xz, zstd, uncompressed = "bzip2", "gzip", "xz", "zstd", "uncompressed"
+
+
+def is_compressed(path) -> str:
+    """Magic-number sniffing, same formats as reference utils.py:126-152."""
+    with open(path, "rb") as fh:
+        sig = fh.read(8)
+    if sig[:2] == b"\x1f\x8b":
+        return Compression.gzip
+    if sig[:3] == b"BZh":
+        return Compression.bzip2
+    if sig[:7] == b"\xfd7zXZ\x00\x00":
+        return Compression.xz
+    if sig[:4] == b"\x28\xb5\x2f\xfd":
+        return Compression.zstd
+    return Compression.uncompressed
+
+
+def read_bytes(path) -> bytes:
+    kind = is_compressed(path)
+    if kind == Compression.gzip:
+        with gzip.open(path, "rb") as fh:
+            return fh.read()
+    if kind == Compression.bzip2:
+        with bz2.open(path, "rb") as fh:
+            return fh.read()
+    if kind == Compression.xz:
+        with lzma.open(path, "rb") as fh:
+            return fh.read()
+    if kind == Compression.zstd:
+        try:
+            from compression import zstd  # Python >= 3.14, as in the reference
+        except ImportError as e:  # pragma: no cover
+            raise RuntimeError("zstd-compressed input needs Python >= 3.14") from e
+        with zstd.open(path, "rb") as fh:
+            return fh.read()
+    with open(path, "rb") as fh:
+        return fh.read()
+
+
+def iter_fasta(path, strip_n: bool = True) -> Iterator[Tuple[str, bytes]]:
+    """Yield (header, sequence bytes) for every record that is non-empty after stripping."""
+    data = read_bytes(path)
+    if b"\r" in data:                       # universal newlines
+        data = data.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+    chunks = (b"\n" + data).split(b"\n>")
+    for rec in chunks[1:]:                  # chunks[0] is whatever precedes the first header line
+        header, _, body = rec.partition(b"\n")
+        seq = body.replace(b"\n", b"")
+        if strip_n:
+            seq = seq.strip(b"nN")
+        if seq:
+            yield header.decode("utf-8", errors="replace"), seq
+
+
+def accession(header: str) -> str:
+    parts = header.split()
+    if not parts:
+        raise ValueError("FASTA record with an empty header line")
+    return parts[0]
+
+
+def check_fasta(path) -> bool:
+    """False if the file has no record or two records share an identifier (reference sequence.py:124-131).
+    Note: like the reference, this pass does NOT strip Ns (only truly empty records are dropped)."""
+    names = [accession(h) for h, _ in iter_fasta(path, strip_n=False)]
+    return bool(names) and len(names) == len(set(names))
+
+
+def window_spans(length: int, single_window: bool = False) -> List[Tuple[int, int]]:
+    """[start, end) of every candidate window of a contig of `length` nt (before the N rule)."""
+    spans = []
+    win = 0
+    while win * WINDOW < length:
+        s, e = win * WINDOW, min((win + 1) * WINDOW, length)
+        if e - s < MIN_TAIL:
+            if win == 0:
+                spans.append((s, e))
+            break
+        spans.append((s, e))
+        win += 1
+        if single_window and win == 1:
+            break
+    return spans
+
+
+@dataclass
+class EncodedFasta:
+    names: np.ndarray        # [n_contigs] str    -- order of appearance (== rows of the outputs)
+    contig_ids: np.ndarray   # [n_windows] int64  -- sorted, one per kept window
+    offsets: np.ndarray      # [n_contigs + 1] int32 -- window range of each contig
+    windows: np.ndarray      # [n_windows, 6000] uint8 -- upper-cased, N-padded ASCII
+
+
+def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = None) -> EncodedFasta:
+    """
+    FASTA -> dense window matrix, the device-resident analogue of generate_data()
+    (reference nn_classification.py:54-82; the TFRecord round trip is gone).
+    """
+    names: List[str] = []
+    ids: List[int] = []
+    pieces: List[bytes] = []
+    for cid, (header, seq) in enumerate(iter_fasta(path, strip_n=True)):
+        names.append(accession(header))
+        for wn, (s, e) in enumerate(window_spans(len(seq), single_window)):
+            raw = seq[s:e]
+            if wn > 0 and raw.count(b"N") > MAX_N:
+                continue
+            up = raw.upper()
+            pieces.append(up if len(up) == WINDOW else up.ljust(WINDOW, b"N"))
+            ids.append(cid)
+    n = len(pieces)
+    if out is not None:
+        assert out.dtype == np.uint8 and out.shape[0] >= n and out.shape[1] == WINDOW
+        win = out[:n]
+        if n:
+            win.reshape(-1)[:] = np.frombuffer(b"".join(pieces), dtype=np.uint8)
+    else:
+        win = (np.frombuffer(b"".join(pieces), dtype=np.uint8).reshape(n, WINDOW) if n
+               else np.zeros((0, WINDOW), np.uint8))
+    cid_arr = np.asarray(ids, dtype=np.int64)
+    counts = np.bincount(cid_arr, minlength=len(names)) if n else np.zeros(len(names), np.int64)
+    offsets = np.zeros(len(names) + 1, dtype=np.int32)
+    np.cumsum(counts, out=offsets[1:])
+    return EncodedFasta(np.array(names), cid_arr, offsets, win)

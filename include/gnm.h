@@ -127,7 +127,9 @@ int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_pro
 /* ---- introspection / test hooks (not needed by a drop-in caller) ------------------------- */
 
 /* Options: "conv_impl" 0 = tcgen05 tensor-core path (default), 1 = fp32 CUDA-core validation
- * kernels; "desc_base_mode" 0/1 = UMMA descriptor base-offset policy for shifted rows. */
+ * kernels (test hook: lets the tensor-core path be checked on the GPU at large batch);
+ * "debug_stop" 0 = full pipeline, 1 = stop after layer 1 + gather#0, 2 = after conv2, 3 = after conv3;
+ * "profile_stages" 1 = record a CUDA event between stages (see gnm_stage_times). */
 int gnm_set_option(gnm_handle* h, const char* name, int value);
 int gnm_get_option(gnm_handle* h, const char* name, int* value);
 
@@ -140,9 +142,10 @@ long long gnm_kernel_launches(gnm_handle* h);
 int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count);
 
 /*
- * Copy an intermediate of the most recent forward step (first min(n, max_batch) windows) to a
- * device buffer as fp32.  which: "y1","y2","y3" [n][5997][128]; "q0","q1" [n][749][128];
- * "mpi0","mpi1" [n][2100]; "h0" [n][256].  Used by the per-kernel parity tests.
+ * Copy an intermediate of the most recent forward step (first n <= max_batch windows) to a device
+ * buffer as fp32.  which: "buf0","buf1" = the two activation buffers [n][5997][128] (after a full
+ * step buf0 = y3, buf1 = y2; with debug_stop = 1, buf0 = y1); "q0","q1" [n][749][128];
+ * "mpi0","mpi1" [n][2100]; "logits" [n][752]; "h0" [n][256].  Used by the per-kernel parity tests.
  */
 int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d_dst, void* stream);
 

@@ -1,0 +1,256 @@
+"""CPU tests of the host side: FASTA/windowing vs reference golden vectors, weights/H5 reader, C-ABI exports,
+module driver output surface (with a stub classifier -- the real one needs a B200)."""
+import ctypes
+import gzip
+import json
+import re
+
+import numpy as np
+import pytest
+
+from genomad_b200 import _paths, engine, h5lite, nn_classification, sequence, utils, weights
+from oracle import tokenizer as T
+
+
+@pytest.fixture(scope="module")
+def enc(golden_dir):
+    return json.loads((golden_dir / "encoder_golden.json").read_text())
+
+
+# ------------------------------------------------------------------------------------------ sequence
+def test_iter_fasta_matches_reference(enc, tmp_path):
+    for name, case in enc["fasta"].items():
+        p = tmp_path / f"{name}.fna"
+        p.write_text(case["text"], newline="")
+        got = [[h, sequence.accession(h), s.decode()] for h, s in sequence.iter_fasta(p)]
+        assert got == [list(r) for r in case["records"]], name
+        assert sequence.check_fasta(p) == case["check_fasta"], name
+
+
+def test_old_mac_newlines_and_gzip(tmp_path):
+    text = ">a x\rACGT\rAC\r>b\rTT\r"
+    p = tmp_path / "mac.fna"
+    p.write_text(text, newline="")
+    assert [(h, s) for h, s in sequence.iter_fasta(p)] == [("a x", b"ACGTAC"), ("b", b"TT")]
+    assert [(h, s.encode()) for h, s in T.read_fasta(p)] == [("a x", b"ACGTAC"), ("b", b"TT")]
+    g = tmp_path / "x.fna.gz"
+    with gzip.open(g, "wt") as fh:
+        fh.write(">a\nNNACGTNN\n")
+    assert list(sequence.iter_fasta(g)) == [("a", b"ACGT")]
+    assert sequence.is_compressed(g) == sequence.Compression.gzip
+
+
+def test_window_spans_match_reference(enc):
+    for case in enc["windows"]:
+        assert [e - s for s, e in sequence.window_spans(case["len"])] == case["multi"]
+        assert [e - s for s, e in sequence.window_spans(case["len"], single_window=True)] == case["single"]
+
+
+def test_encode_fasta_matches_oracle(enc, tmp_path):
+    rng = np.random.default_rng(3)
+    recs = []
+    for i, ln in enumerate([10000, 400, 2499, 14500, 6000, 30000, 8499]):
+        s = np.frombuffer(b"ACGTNacgtnRY", np.uint8)[rng.choice(12, ln, p=[.2, .2, .2, .2, .04, .03, .03, .03, .03, .01, .02, .01])]
+        recs.append(f">c{i} some description\n" + "\n".join(s.tobytes().decode()[k:k + 70] for k in range(0, ln, 70)))
+    for case in enc["nrule"]:
+        recs.append(f">{case['name']}\n{case['raw']}")
+    p = tmp_path / "mix.fna"
+    p.write_text("\n".join(recs) + "\n")
+    for single in (False, True):
+        e = sequence.encode_fasta(p, single_window=single)
+        names, ids, ascii_arr, _tok = T.encode_fasta(p, single_window=single)
+        assert list(e.names) == list(names)
+        assert np.array_equal(e.contig_ids, ids)
+        assert np.array_equal(e.windows, ascii_arr)
+        assert e.offsets[-1] == len(ids) and np.all(np.diff(e.offsets) >= 1)
+    for case in enc["nrule"]:
+        q = tmp_path / "n.fna"
+        q.write_text(f">x\n{case['raw']}\n")
+        assert len(sequence.encode_fasta(q).contig_ids) == len(case["kept"]), case["name"]
+
+
+# ------------------------------------------------------------------------------------------ weights
+def test_weights_npz_and_shapes(weights_npz):
+    w = weights.load_weights(weights_npz)
+    assert w["c1w"].shape == (6, 257, 128) and w["ig1_random_patches"].dtype == np.int32
+    # spot values recorded from the H5 during the survey
+    assert np.allclose(w["c1w"][0, 0, :3], [-0.0358333, 0.0309101, 0.0279195], atol=1e-7)
+    assert np.allclose(w["d2b"], [0.0138235, -0.0161939, -0.0010647], atol=1e-7)
+    assert w["ig0_random_patches"][0, :, 0].tolist() == [296, 948, 3644, 4375]
+    assert w["ig1_random_patches"][1, :, 0].tolist() == [958, 1714, 3162, 5978]
+    assert float(np.abs(w["ig0_w_mult"]).max()) < 1e-30          # the shipped patch weights are numerically dead
+    z = np.load(weights_npz)
+    assert str(z["__sha256__"]) == "834bcb03aeb1ff484dc7c1f7c00fb951708a91ed03d8a233cd176390930761a1"
+
+
+def test_h5lite_reads_reference_file_if_present(weights_npz):
+    ref = "/root/reference/genomad/data/nn_classifier.h5"
+    import os
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present on this box")
+    f = h5lite.H5File(ref)
+    z = np.load(weights_npz)
+    assert len(f.datasets) == 32
+    for k, v in f.datasets.items():
+        assert np.array_equal(v, z[k]), k
+    assert f.offsets["/model/conv1d/kernel:0"] == 1087096
+    assert f.attrs["/"]["keras_version"] == "2.7.0"
+    w = weights.load_weights(ref)
+    assert np.array_equal(w["c2w"], z["/model/conv1d_1/kernel:0"])
+
+
+def test_weights_validation_rejects_bad_shapes(weights_npz):
+    z = np.load(weights_npz)
+    raw = {k: z[k] for k in z.files if k.startswith("/")}
+    raw["/model/conv1d_1/kernel:0"] = raw["/model/conv1d_1/kernel:0"][:5]
+    with pytest.raises(ValueError):
+        weights._validate(raw)
+
+
+# ------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol(repo_root):
+    header = (repo_root / "include" / "gnm.h").read_text()
+    declared = set(re.findall(r"\b(gnm_[a-z_0-9]+)\s*\(", header))
+    assert declared >= {"gnm_create", "gnm_encode", "gnm_forward_ascii", "gnm_segment_mean", "gnm_classify_host"}
+    lib = engine.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libgnm.so does not export {name}"
+    assert set(engine.EXPORTS) == declared
+    assert b"sm_100a" in lib.gnm_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.GnmError):
+        engine.Classifier()
+    # C ABI level: create must fail loudly without a device
+    lib = engine.load_library()
+    w = weights.load_weights()
+    cw = weights.to_c_struct(w, engine._Weights, engine._IglooW, engine._BnW)
+    h = ctypes.c_void_p()
+    assert lib.gnm_create(0, ctypes.byref(cw), 8, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.gnm_last_error() or b"CUDA" in lib.gnm_last_error()
+
+
+# ------------------------------------------------------------------------------------------ module driver
+class _StubClassifier:
+    """Deterministic stand-in (hash of the window bytes) so the driver's plumbing can run without a GPU."""
+    device = 0
+    calls = 0
+
+    def classify_host(self, windows):
+        _StubClassifier.calls += 1
+        s = windows.astype(np.float64).sum(axis=1)
+        p = np.stack([np.sin(s) ** 2, np.cos(s) ** 2 * 0.5, np.cos(s) ** 2 * 0.5], axis=1)
+        return p.astype(np.float32)
+
+
+@pytest.fixture
+def stub_driver(monkeypatch):
+    _StubClassifier.calls = 0
+    monkeypatch.setattr(nn_classification, "_make_classifier", lambda batch_size, device: _StubClassifier())
+
+    def fake_classify(clf, windows, offsets, info, contig_reduce="gather"):
+        return T.segment_mean(clf.classify_host(windows), np.repeat(np.arange(len(offsets) - 1), np.diff(offsets)),
+                              len(offsets) - 1)
+    monkeypatch.setattr(nn_classification, "_classify_windows", fake_classify)
+    return _StubClassifier
+
+
+def _write_fasta(path, n=5, seed=0):
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as fh:
+        for i in range(n):
+            s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 10000)].tobytes().decode()
+            fh.write(f">contig_{i:03d} d\n")
+            for k in range(0, len(s), 60):
+                fh.write(s[k:k + 60] + "\n")
+
+
+def test_main_output_surface_and_restart(tmp_path, stub_driver, capsys):
+    fa = tmp_path / "sample.fna"
+    _write_fasta(fa)
+    out = tmp_path / "out"
+    nn_classification.main(fa, out, False, 128, False, 4, True, False)
+    o = _paths.NNOutputs("sample", out)
+    assert o.nn_classification_log.exists() and o.nn_classification_execution_info.exists()
+    info = json.loads(o.nn_classification_execution_info.read_text())
+    assert set(info) == {"module", "input", "input_md5", "start_time", "parameters"}
+    assert info["module"] == "nn_classification" and info["parameters"] == {"single_window": False}
+    assert info["input_md5"] == utils.get_md5(fa) and info["input"] == "sample.fna"
+    z = np.load(o.nn_classification_npz_output)
+    assert set(z.files) == {"contig_names", "predictions"}
+    assert z["predictions"].dtype == np.float32 and z["predictions"].shape == (5, 3)
+    assert list(z["contig_names"]) == [f"contig_{i:03d}" for i in range(5)]
+    ids = np.load(o.seq_window_id_output)
+    assert set(ids.files) == {"contig_names", "contig_ids"} and ids["contig_ids"].tolist() == [0, 0, 1, 1, 2, 2, 3, 3, 4, 4]
+    lines = o.nn_classification_output.read_text().splitlines()
+    assert lines[0] == "seq_name\tchromosome_score\tplasmid_score\tvirus_score"
+    for name, row, line in zip(z["contig_names"], z["predictions"], lines[1:]):
+        assert line == f"{name}\t" + "\t".join(f"{x:.4f}" for x in row)      # format(np.float32, '.4f'), as the reference
+    assert "finished" in o.nn_classification_log.read_text()
+    # second run: everything is skipped
+    calls = stub_driver.calls
+    nn_classification.main(fa, out, False, 128, False, 4, False, False)
+    assert stub_driver.calls == calls
+    assert "Skipping sequence classification" in o.nn_classification_log.read_text()
+    # --restart recomputes; changed parameters recompute; --cleanup removes the encoded dir
+    nn_classification.main(fa, out, False, 128, True, 4, False, False)
+    assert stub_driver.calls == calls + 1
+    nn_classification.main(fa, out, True, 128, False, 4, False, True)
+    assert stub_driver.calls == calls + 2
+    assert not o.encoded_sequences_dir.exists()
+    assert np.load(o.nn_classification_npz_output)["predictions"].shape == (5, 3)
+
+
+def test_main_errors_exit_1(tmp_path, stub_driver):
+    dup = tmp_path / "dup.fna"
+    dup.write_text(">a\nACGT\n>a\nACGT\n")
+    with pytest.raises(SystemExit) as e:
+        nn_classification.main(dup, tmp_path / "o1", False, 128, False, 1, False, False)
+    assert e.value.code == 1
+    empty = tmp_path / "empty.fna"
+    empty.write_text("")
+    with pytest.raises(SystemExit) as e:
+        nn_classification.main(empty, tmp_path / "o2", False, 128, False, 1, False, False)
+    assert e.value.code == 1
+    only_n = tmp_path / "n.fna"
+    only_n.write_text(">a\nNNNN\n")
+    with pytest.raises(SystemExit) as e:
+        nn_classification.main(only_n, tmp_path / "o3", False, 128, False, 1, False, False)
+    assert e.value.code == 1
+
+
+def test_main_compressed_prefix_and_provirus_twin(tmp_path, stub_driver):
+    fa = tmp_path / "s.fna"
+    _write_fasta(fa, n=2)
+    gz = tmp_path / "sample2.fna.gz"
+    gz.write_bytes(gzip.compress(fa.read_bytes()))
+    out = tmp_path / "out"
+    out.mkdir()
+    o = _paths.NNOutputs("sample2", out)
+    # fake a finished find-proviruses run on the same input
+    o.find_proviruses_dir.mkdir()
+    utils.write_execution_info("find_proviruses", gz, {}, o.find_proviruses_execution_info)
+    o.find_proviruses_output.write_text("seq_name\tx\ncontig_000|provirus_1_5000\t1\n")
+    o.find_proviruses_nucleotide_output.write_text(">contig_000|provirus_1_5000\n" + "ACGT" * 1250 + "\n")
+    o.find_proviruses_proteins_output.write_text("")
+    o.find_proviruses_genes_output.write_text("")
+    nn_classification.main(gz, out, False, 64, False, 1, False, False)
+    assert o.nn_classification_npz_output.exists()
+    z = np.load(o.provirus_nn_classification_npz_output)
+    assert set(z.files) == {"provirus_names", "predictions"} and z["predictions"].shape == (1, 3)
+    assert set(np.load(o.provirus_window_id_output).files) == {"provirus_names", "provirus_ids"}
+    assert o.provirus_nn_classification_output.read_text().splitlines()[1].startswith("contig_000|provirus_1_5000\t")
+
+
+def test_cli_options_match_reference():
+    from click.testing import CliRunner
+    from genomad_b200 import cli
+    r = CliRunner().invoke(cli.cli, ["nn-classification", "--help"])
+    assert r.exit_code == 0
+    for opt in ("--restart", "--threads", "-t", "--verbose", "--quiet", "-v", "-q", "--cleanup", "--single-window",
+                "--batch-size", "INPUT", "OUTPUT"):
+        assert opt in r.output, opt
