@@ -373,7 +373,6 @@ static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, 
 // One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
 static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
                         cudaStream_t st) {
-  h->timer.names.clear();
   h->last_n = n;
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   timer_mark(h, "embed_conv1", st);
@@ -533,7 +532,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
-  else if (k == "profile_stages") h->profile_stages = value ? 1 : 0;
+  else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;
 }
@@ -553,16 +552,19 @@ extern "C" long long gnm_kernel_launches(gnm_handle* h) { return h ? h->launches
 extern "C" int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count) {
   if (!h || !count) return fail("null argument");
   GNM_CUDA(cudaSetDevice(h->device));
-  const int ns = static_cast<int>(h->timer.names.size()) - 1;
-  if (ns <= 0) { *count = 0; return 0; }
-  GNM_CUDA(cudaEventSynchronize(h->timer.events[ns]));
+  const int ns = static_cast<int>(h->timer.names.size());
   const int cap = *count;
+  *count = 0;
+  if (ns < 2) return 0;
+  GNM_CUDA(cudaEventSynchronize(h->timer.events[ns - 1]));
   int k = 0;
-  for (; k < ns && k < cap; ++k) {
+  for (int i = 0; i + 1 < ns && k < cap; ++i) {
+    if (std::strcmp(h->timer.names[i], "end") == 0) continue;     // gap between two recorded steps
     float t = 0.f;
-    GNM_CUDA(cudaEventElapsedTime(&t, h->timer.events[k], h->timer.events[k + 1]));
-    if (names) names[k] = h->timer.names[k];
+    GNM_CUDA(cudaEventElapsedTime(&t, h->timer.events[i], h->timer.events[i + 1]));
+    if (names) names[k] = h->timer.names[i];
     if (ms) ms[k] = t;
+    ++k;
   }
   *count = k;
   return 0;

@@ -225,9 +225,10 @@ class Classifier:
 
     # ------------------------------------------------------------------ introspection
     def stage_times(self) -> List[Tuple[str, float]]:
-        names = (C.c_char_p * 32)()
-        ms = (C.c_float * 32)()
-        cnt = C.c_int(32)
+        cap = 16384
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        cnt = C.c_int(cap)
         _check(self.lib, self.lib.gnm_stage_times(self._h, names, ms, C.byref(cnt)))
         return [(names[i].decode(), float(ms[i])) for i in range(cnt.value)]
 

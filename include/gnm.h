@@ -136,9 +136,10 @@ int gnm_get_option(gnm_handle* h, const char* name, int* value);
 /* Number of kernels this library has launched through handle h (monotonic). */
 long long gnm_kernel_launches(gnm_handle* h);
 
-/* Per-stage device time of the most recent gnm_forward_* step, in milliseconds (CUDA events;
- * requires option "profile_stages" = 1, which serialises the step).  names/ms arrays of length
- * >= *count on input; *count on output = number of stages written. */
+/* Per-stage device times (CUDA events recorded on the caller's stream between the stages of every
+ * gnm_forward_* / gnm_classify_host step) since option "profile_stages" was last set to 1.
+ * names/ms: arrays of capacity *count on input; *count on output = number of (stage, ms) records
+ * written, in execution order, one per stage per step.  Synchronises on the last recorded event. */
 int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count);
 
 /*

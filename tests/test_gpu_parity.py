@@ -1,0 +1,227 @@
+"""
+GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI of libgnm.so,
+against the CPU oracle and the committed golden fixtures.
+
+Tolerances: tokens are bit-exact; per-window probabilities are within 1e-4 (absolute) of the fp32 oracle
+-- the bar BASELINE.json's north_star states -- and class calls (argmax) are identical.
+"""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import igloo_model as M
+from oracle import tokenizer as T
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _families(n, seed):
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    import precision_study
+    return precision_study.make_windows(n, seed)
+
+
+@pytest.fixture(scope="module")
+def shipped(weights_npz):
+    return M.load_npz_weights(weights_npz)
+
+
+@pytest.fixture(scope="module")
+def clf():
+    from genomad_b200 import engine
+    c = engine.Classifier(None, device=0, max_batch=256)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def clf_syn(shipped):
+    from genomad_b200 import engine
+    c = engine.Classifier(M.synthetic_igloo_weights(shipped), device=0, max_batch=64)
+    yield c
+    c.close()
+
+
+def _oracle_probs(tok, w, dtype=torch.float32, bs=32):
+    return np.concatenate([M.forward(tok[i:i + bs], w, dtype) for i in range(0, len(tok), bs)])
+
+
+# ------------------------------------------------------------------------------------------ encoder
+def test_encode_bitexact_reference_golden(clf, golden_dir):
+    enc = json.loads((golden_dir / "encoder_golden.json").read_text())
+    ref = np.load(golden_dir / "encoder_batch_tokens.npz")["tokens"]       # produced by the REAL reference tokenizer
+    a = np.frombuffer(b"".join(r.upper().encode("ascii").ljust(6000, b"N") for r in enc["batch"]["raw"]),
+                      np.uint8).reshape(-1, 6000)
+    tok = clf.encode(torch.from_numpy(a.copy()).cuda()).cpu().numpy()
+    assert tok.dtype == np.uint16 and np.array_equal(tok, ref)
+    assert hashlib.sha256(tok.tobytes()).hexdigest() == enc["batch"]["tokens_sha256"]
+
+
+def test_encode_adversarial_bytes(clf):
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 256, (257, 6000), dtype=np.uint8)                # every byte value, incl. lowercase / IUPAC / NUL
+    a[1] = ord("N"); a[2] = ord("A"); a[3, ::7] = ord("n"); a[4, :3] = ord("N"); a[5, -3:] = ord("N")
+    tok = clf.encode(torch.from_numpy(a).cuda()).cpu().numpy()
+    assert np.array_equal(tok, T.tokenize_windows(a))
+    assert tok[1].max() == 0 and tok[2].min() == 1 == tok[2].max()
+    assert clf.encode(torch.empty((0, 6000), dtype=torch.uint8, device="cuda")).shape == (0, 5997)
+
+
+# ------------------------------------------------------------------------------------------ model
+def test_forward_matches_frozen_golden(clf, golden_dir):
+    g = np.load(golden_dir / "model_golden.npz")
+    p = clf.predict_ascii(torch.from_numpy(g["ascii"]).cuda()).cpu().numpy()
+    assert np.abs(p - g["shipped_fp32"]).max() <= TOL
+    assert np.abs(p - g["shipped_fp64"]).max() <= TOL
+    assert np.array_equal(p.argmax(1), g["shipped_fp64"].argmax(1))
+    assert np.allclose(p.sum(1), 1.0, atol=1e-6)
+
+
+def test_forward_synthetic_weights_match_frozen_golden(clf_syn, golden_dir):
+    """Non-degenerate patch/attention weights: a wrong gather or softmax cannot hide here."""
+    g = np.load(golden_dir / "model_golden.npz")
+    p = clf_syn.predict_ascii(torch.from_numpy(g["ascii"]).cuda()).cpu().numpy()
+    assert np.abs(p - g["synthetic_fp32"]).max() <= TOL
+    assert np.array_equal(p.argmax(1), g["synthetic_fp64"].argmax(1))
+
+
+def test_forward_parity_mixed_families(clf, shipped):
+    a = _families(96, seed=21)                      # iid, GC-skew, tandem repeats, N tails, Markov, homopolymer, N islands
+    tok = T.tokenize_windows(a)
+    ref = _oracle_probs(tok, shipped)
+    p = clf.predict_ascii(torch.from_numpy(a).cuda()).cpu().numpy()
+    assert np.abs(p - ref).max() <= TOL
+    assert np.array_equal(p.argmax(1), ref.argmax(1))
+    p2 = clf.predict_tokens(torch.from_numpy(tok.view(np.int16)).cuda().view(torch.uint16)).cpu().numpy()
+    assert np.array_equal(p, p2)                    # fused encode == separate encode, bitwise
+
+
+def test_stagewise_parity_synthetic(clf_syn, shipped):
+    w = M.synthetic_igloo_weights(shipped)
+    a = _families(8, seed=5)
+    tok = T.tokenize_windows(a)
+    _, it = M.forward(tok, w, torch.float32, return_intermediates=True)
+    da = torch.from_numpy(a).cuda()
+
+    def close(name, got, ref, rel):
+        ref = ref.numpy() if hasattr(ref, "numpy") else ref
+        d = np.abs(got.cpu().numpy().astype(np.float64) - ref).max()
+        assert d <= rel * max(1.0, np.abs(ref).max()), (name, d)
+
+    try:
+        clf_syn.set_option("debug_stop", 1); clf_syn.predict_ascii(da); torch.cuda.synchronize()
+        close("y1", clf_syn.debug_fetch("buf0", 8), it["y1"], 2e-6)
+        close("mpi0", clf_syn.debug_fetch("mpi0", 8), it["ig0"]["mpi"], 1e-5)
+        clf_syn.set_option("debug_stop", 2); clf_syn.predict_ascii(da); torch.cuda.synchronize()
+        close("y2", clf_syn.debug_fetch("buf1", 8), it["y2"], 1e-5)
+        close("q0", clf_syn.debug_fetch("q0", 8), it["ig0"]["q"], 1e-5)
+        clf_syn.set_option("debug_stop", 3); clf_syn.predict_ascii(da); torch.cuda.synchronize()
+        close("y3", clf_syn.debug_fetch("buf0", 8), it["y3"], 1e-5)
+    finally:
+        clf_syn.set_option("debug_stop", 0)
+    clf_syn.predict_ascii(da); torch.cuda.synchronize()
+    close("q1", clf_syn.debug_fetch("q1", 8), it["ig1"]["q"], 1e-5)
+    close("mpi1", clf_syn.debug_fetch("mpi1", 8), it["ig1"]["mpi"], 2e-5)
+    close("h0", clf_syn.debug_fetch("h0", 8), it["h0"], 1e-5)
+
+
+def test_tensor_core_path_vs_cuda_core_validation_kernels(clf):
+    """512 windows: tcgen05 fp16x3 path vs the independent fp32 FFMA kernels, both on the GPU."""
+    a = torch.from_numpy(_families(512, seed=33)).cuda()
+    p_tc = clf.predict_ascii(a).clone()
+    try:
+        clf.set_option("conv_impl", 1)
+        p_ref = clf.predict_ascii(a).clone()
+    finally:
+        clf.set_option("conv_impl", 0)
+    assert (p_tc - p_ref).abs().max().item() <= 5e-5
+    assert torch.equal(p_tc.argmax(1), p_ref.argmax(1))
+
+
+def test_batching_invariance_and_host_path(clf):
+    a = _families(300, seed=2)                                            # > max_batch (256): two internal steps
+    da = torch.from_numpy(a).cuda()
+    p_all = clf.predict_ascii(da).cpu().numpy()
+    p_one = np.concatenate([clf.predict_ascii(da[i:i + 1]).cpu().numpy() for i in (0, 7, 255, 256, 299)])
+    assert np.array_equal(p_one, p_all[[0, 7, 255, 256, 299]])            # position in the batch does not matter
+    perm = np.random.default_rng(0).permutation(300)
+    assert np.array_equal(clf.predict_ascii(da[torch.from_numpy(perm).cuda()]).cpu().numpy(), p_all[perm])
+    assert np.array_equal(clf.classify_host(a), p_all)                    # host-buffer entry point == device entry point
+    assert clf.classify_host(a[:0]).shape == (0, 3)
+    n0 = clf.kernel_launches
+    clf.predict_ascii(da[:4])
+    assert clf.kernel_launches - n0 == 13                                 # our kernels really launched
+
+
+def test_segment_mean_and_sum(clf):
+    rng = np.random.default_rng(4)
+    counts = np.array([1, 167, 0, 2, 13, 1, 1, 40], np.int64)             # includes an empty segment
+    W = int(counts.sum())
+    probs = rng.random((W, 3)).astype(np.float32)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dp, do = torch.from_numpy(probs).cuda(), torch.from_numpy(offsets).cuda()
+    mean = clf.segment_mean(dp, do).cpu().numpy()
+    ref = T.segment_mean(probs, np.repeat(np.arange(len(counts)), counts), len(counts))
+    assert np.array_equal(mean, ref)                                      # same sequential fp32 order -> bitwise
+    s4 = clf.segment_sum(dp, do).cpu().numpy()
+    assert np.array_equal(s4[:, 3], counts.astype(np.float32))
+    assert np.allclose(s4[:, :3] / np.maximum(s4[:, 3:4], 1), ref, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_config2_scale_properties():
+    """BASELINE config 2 shape (batch 1024) at reduced length: 20 steps of 1024 windows drawn from a 1024-window
+    pool in a different order each step -> results are a pure function of the window (idempotence), rows are
+    probabilities, and the checksum of checksums is order-independent."""
+    from genomad_b200 import engine
+    c = engine.Classifier(None, device=0, max_batch=1024)
+    pool = torch.from_numpy(_families(1024, seed=77)).cuda()
+    base = c.predict_ascii(pool).clone()
+    assert torch.all(base >= 0) and torch.all(base <= 1)
+    assert (base.sum(1) - 1).abs().max().item() < 1e-5
+    g = torch.Generator(device="cpu").manual_seed(0)
+    total = torch.zeros(3, dtype=torch.float64, device="cuda")
+    for _ in range(20):
+        perm = torch.randperm(1024, generator=g).cuda()
+        p = c.predict_ascii(pool[perm])
+        assert torch.equal(p, base[perm])
+        total += p.double().sum(0)
+    assert torch.allclose(total, base.double().sum(0) * 20, rtol=0, atol=1e-9)
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------ module on the GPU (config 1)
+def test_cli_config1_end_to_end(tmp_path, shipped):
+    """BASELINE config 1: 100 synthetic 10 kb contigs through the CLI; TSV/NPZ vs the CPU oracle pipeline."""
+    from click.testing import CliRunner
+    from genomad_b200 import cli, _paths
+    rng = np.random.default_rng(0)
+    fa = tmp_path / "cfg1.fna"
+    with open(fa, "w") as fh:
+        for i in range(100):
+            s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 10000)].tobytes().decode()
+            fh.write(f">contig_{i:03d}\n")
+            for k in range(0, 10000, 60):
+                fh.write(s[k:k + 60] + "\n")
+    out = tmp_path / "out"
+    r = CliRunner().invoke(cli.cli, ["nn-classification", "--quiet", "--batch-size", "128", str(fa), str(out)])
+    assert r.exit_code == 0, r.output
+    o = _paths.NNOutputs("cfg1", out)
+    z = np.load(o.nn_classification_npz_output)
+    names, ids, ascii_arr, tok = T.encode_fasta(fa)
+    assert len(ids) == 200 and list(z["contig_names"]) == list(names)
+    ref = T.segment_mean(_oracle_probs(tok, shipped), ids)
+    assert np.abs(z["predictions"] - ref).max() <= TOL
+    assert np.array_equal(z["predictions"].argmax(1), ref.argmax(1))
+    lines = o.nn_classification_output.read_text().splitlines()
+    assert len(lines) == 101 and lines[0].split("\t") == ["seq_name", "chromosome_score", "plasmid_score", "virus_score"]
+    for line, name, row in zip(lines[1:], names, ref):
+        f = line.split("\t")
+        assert f[0] == name and all(abs(float(x) - y) <= TOL + 5e-5 for x, y in zip(f[1:], row))
