@@ -52,7 +52,7 @@ struct gnm_handle {
   int profile_stages = 0;
   // weights on device
   float* conv1_table = nullptr; float* conv1_bias = nullptr;
-  __half* wpack[3] = {nullptr, nullptr, nullptr};   // conv2(+wv0), conv3, wv1 -- TMA stage order
+  __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, wv0, wv1 -- TMA stage order
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
@@ -73,7 +73,7 @@ struct gnm_handle {
   cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
   DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
   CUtensorMap tm_act[2];
-  CUtensorMap tm_w[3];
+  CUtensorMap tm_w[4];
   int last_n = 0;
   StageTimer timer;
   std::vector<float> stage_ms;
@@ -178,20 +178,23 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (dev_upload(h, &h->conv1_table, w->conv1_kernel, static_cast<size_t>(kTaps) * kVocab * kC)) return 1;
   if (dev_upload(h, &h->conv1_bias, w->conv1_bias, kC)) return 1;
 
-  // ---- tensor-core weight packs (consumption order of conv_tc_kernel)
+  // ---- tensor-core weight packs, in the order the kernels consume their 16 KB stages
   {
     const float* convw[2] = {w->conv2_kernel, w->conv3_kernel};
     for (int L = 0; L < 2; ++L) {
-      std::vector<__half> pk;
-      pk.reserve(static_cast<size_t>(28) * 128 * 64);
-      for (int tap = 0; tap < kTaps; ++tap) pack_matrix_stages(pk, convw[L] + static_cast<size_t>(tap) * kC * kC);
-      if (L == 0) pack_matrix_stages(pk, w->igloo[0].w_v);   // conv2 kernel also projects its INPUT (y1) with w_v#0
+      std::vector<__half> pk;                              // conv2t_kernel: (K-half, tap, weight hi/lo)
+      pk.reserve(static_cast<size_t>(kConv2tStages) * 128 * 64);
+      for (int kh = 0; kh < 2; ++kh)
+        for (int tap = 0; tap < kTaps; ++tap)
+          for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, w_lo, kh);
       if (dev_upload(h, &h->wpack[L], pk.data(), pk.size())) return 1;
       if (dev_upload(h, &h->conv_w32[L], convw[L], static_cast<size_t>(kTaps) * kC * kC)) return 1;
     }
-    std::vector<__half> pk;
-    pack_matrix_stages(pk, w->igloo[1].w_v);
-    if (dev_upload(h, &h->wpack[2], pk.data(), pk.size())) return 1;
+    for (int s = 0; s < 2; ++s) {                          // conv_tc_kernel<0,true>: (hi,k0) (hi,k1) (lo,k0) (lo,k1)
+      std::vector<__half> pk;
+      pack_matrix_stages(pk, w->igloo[s].w_v);
+      if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
+    }
     if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
     if (dev_upload(h, &h->conv_bias[1], w->conv3_bias, kC)) return 1;
   }
@@ -257,13 +260,13 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (get_encode_fn(&enc)) return 1;
   for (int i = 0; i < 2; ++i)
     if (make_act_map(enc, &h->tm_act[i], h->ybuf[i], max_batch)) return 1;
-  if (make_w_map(enc, &h->tm_w[0], h->wpack[0], 28)) return 1;
-  if (make_w_map(enc, &h->tm_w[1], h->wpack[1], 24)) return 1;
+  if (make_w_map(enc, &h->tm_w[0], h->wpack[0], kConv2tStages)) return 1;
+  if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConv2tStages)) return 1;
   if (make_w_map(enc, &h->tm_w[2], h->wpack[2], 4)) return 1;
+  if (make_w_map(enc, &h->tm_w[3], h->wpack[3], 4)) return 1;
 
   // ---- opt in to large dynamic shared memory
-  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
-  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2tSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
@@ -307,22 +310,27 @@ static void timer_mark(gnm_handle* h, const char* name, cudaStream_t st) {
   t.names.push_back(name);
 }
 
-static int launch_conv_tc(gnm_handle* h, int which, int in_buf, int n, cudaStream_t st) {
+// layer 0: conv2 (y[in] -> y[1-in]); layer 1: conv3
+static int launch_conv_tc(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t st) {
+  ConvTcParams p;
+  p.n_tiles = n * kUnitsPerWin;                  // two-tile units
+  p.status = h->status;
+  p.bias = h->conv_bias[layer];
+  p.y_out = h->ybuf[1 - in_buf];
+  p.q_out = nullptr;
+  const int grid = std::min(h->num_sms, p.n_tiles);
+  conv2t_kernel<<<grid, kConvThreads, kConv2tSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
+  return check_launch(h, "conv2t_kernel");
+}
+// q[s] = maxpool8(y[buf] @ w_v#s)
+static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   ConvTcParams p;
   p.n_tiles = n * kTilesPerWin;
   p.status = h->status;
+  p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[s];
   const int grid = std::min(h->num_sms, p.n_tiles);
-  if (which == 0) {          // conv2: y[in] -> y[1-in], q0 from the input
-    p.bias = h->conv_bias[0]; p.y_out = h->ybuf[1 - in_buf]; p.q_out = h->q[0];
-    conv_tc_kernel<6, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[0], p);
-  } else if (which == 1) {   // conv3
-    p.bias = h->conv_bias[1]; p.y_out = h->ybuf[1 - in_buf]; p.q_out = nullptr;
-    conv_tc_kernel<6, false><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[1], p);
-  } else {                   // w_v#1 + max-pool on y3
-    p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[1];
-    conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[in_buf], h->tm_w[2], p);
-  }
-  return check_launch(h, "conv_tc_kernel");
+  conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
+  return check_launch(h, "conv_tc_kernel<0,true>");
 }
 
 static int ensure_scratch(gnm_handle* h) {
@@ -385,14 +393,16 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   if (launch_gather(h, 0, 0, n, st)) return 1;
   if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
   if (h->conv_impl == 0) {
-    timer_mark(h, "conv2+wv0", st);
-    if (launch_conv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1), q0
+    timer_mark(h, "wv0", st);
+    if (launch_wv_tc(h, 0, 0, n, st)) return 1;               // y1 (buf0) -> q0
+    timer_mark(h, "conv2", st);
+    if (launch_conv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1)
     if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
     timer_mark(h, "conv3", st);
     if (launch_conv_tc(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
     if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
     timer_mark(h, "wv1", st);
-    if (launch_conv_tc(h, 2, 0, n, st)) return 1;             // y3 (buf0) -> q1
+    if (launch_wv_tc(h, 1, 0, n, st)) return 1;               // y3 (buf0) -> q1
   } else {
     timer_mark(h, "wv0(ref)", st);
     if (launch_wv_ref(h, 0, 0, n, st)) return 1;

@@ -244,4 +244,193 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
   }
 }
 
+
+// =================================================================================================
+// conv2t: the production Conv1D kernel.  Same math as conv_tc_kernel<6,false>, different schedule:
+// one work unit = TWO adjacent 128-position tiles of a window (24 units per window), so every 16 KB
+// weight stage fetched from L2 feeds 2x the MMAs (measured on the 1-tile kernel: tensor pipe 36 %
+// busy, stalled on the weight ring; profiles/r01_conv_1tile_ncu.md).
+//
+//   * activation slab: 2 x 136-row TMA boxes per (plane, K-half) = rows t0-5 .. t0+266; tile b's
+//     taps start 128 rows further down the same slab.
+//   * the slab is "double-buffered by K-half": stages are ordered K-half-major (all taps of
+//     channels 0..63, then all taps of channels 64..127), so the k0 regions are free again after
+//     the first 12 stages and are reloaded for the NEXT unit while the k1 stages run, and vice versa.
+//   * separate producer threads for activations (warp 3) and weights (warp 0) so neither blocks the other;
+//     weight ring = 5 stages.
+//   * accumulators: 2 sets x {tile a, tile b} x 128 TMEM columns = all 512 columns, so the epilogue
+//     of unit u overlaps the MMAs of unit u+1.
+// =================================================================================================
+constexpr int kUnitsPerWin  = (kTilesPerWin + 1) / 2;             // 24
+constexpr int kSlab2Rows    = 2 * kSlabRows;                      // 272
+constexpr int kA2Region     = kSlab2Rows * 128;                   // 34816 B
+constexpr int kA2Bytes      = 4 * kA2Region;                      // 139264 B (hi.k0 hi.k1 lo.k0 lo.k1)
+constexpr int kNumB2Stages  = 5;
+constexpr int kConv2tSmem   = kA2Bytes + kNumB2Stages * kBStage + 2048;
+constexpr int kConv2tStages = 24;                                 // (K-half, tap, weight hi/lo)
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
+              const ConvTcParams p) {
+  constexpr uint32_t kIdesc = umma_idesc_f16(kTileM, kC);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_a = smem;                                   // 4 regions x 272 rows x 128 B
+  uint8_t* s_b = smem + kA2Bytes;                        // 5 x 16 KB
+  float* s_bias = reinterpret_cast<float*>(s_b + kNumB2Stages * kBStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kC);
+  uint64_t* a_full = bars;            // [2]  per K-half
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* b_full = bars + 4;        // [5]
+  uint64_t* b_empty = bars + 9;       // [5]
+  uint64_t* acc_full = bars + 14;     // [2]
+  uint64_t* acc_empty = bars + 16;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.n_tiles;      // for this kernel n_tiles carries n_windows * 24
+
+  if (threadIdx.x < kC) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_act);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kNumB2Stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(s_tmem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 3 && lane == 0) {
+    // ===================================================================== activation producer
+    int it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int w = unit / kUnitsPerWin;
+      const int t0 = (unit - w * kUnitsPerWin) * (2 * kTileM);
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {
+        mbar_wait(&a_empty[kh], ph ^ 1, p.status, 100 + kh);
+        mbar_arrive_expect_tx(&a_full[kh], 2 * kA2Region);
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          uint8_t* dst = s_a + (plane * 2 + kh) * kA2Region;
+          const int c0 = plane * kC + kh * 64;
+          tma_load_3d(dst, &tm_act, &a_full[kh], c0, t0 - 5, w);
+          tma_load_3d(dst + kARegion, &tm_act, &a_full[kh], c0, t0 - 5 + kSlabRows, w);
+        }
+      }
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ===================================================================== weight producer
+    uint32_t bcount = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      for (int q = 0; q < kConv2tStages; ++q, ++bcount) {
+        const int s = bcount % kNumB2Stages;
+        const uint32_t bphase = (bcount / kNumB2Stages) & 1;
+        mbar_wait(&b_empty[s], bphase ^ 1, p.status, 110 + s);
+        mbar_arrive_expect_tx(&b_full[s], kBStage);
+        tma_load_2d(s_b + s * kBStage, &tm_w, &b_full[s], 0, q * 128);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================================== MMA issuer
+    uint32_t bcount = 0;
+    int it = 0;
+    const uint32_t a_base = smem_u32(s_a);
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t accphase = (it >> 1) & 1;
+      const uint32_t aph = it & 1;
+      const uint32_t acc0 = tmem_base + as * 256;          // tile a; tile b = +128
+      mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 200 + as);
+      for (int q = 0; q < kConv2tStages; ++q, ++bcount) {
+        const int kh = q / 12, r = q - kh * 12, tap = r >> 1, w_lo = r & 1;
+        if (r == 0) mbar_wait(&a_full[kh], aph, p.status, 210 + kh);
+        const int s = bcount % kNumB2Stages;
+        const uint32_t bphase = (bcount / kNumB2Stages) & 1;
+        mbar_wait(&b_full[s], bphase, p.status, 220 + s);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(s_b + s * kBStage);
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          const uint32_t a_hi = a_base + kh * kA2Region + (tile * kTileM + tap) * 128;
+          const uint32_t a_lo = a_base + (2 + kh) * kA2Region + (tile * kTileM + tap) * 128;
+          const uint32_t acc = acc0 + tile * 128;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t bdesc = umma_desc_sw128(b_addr + kk * 32);
+            umma_f16(acc, umma_desc_sw128(a_hi + kk * 32), bdesc, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+            if (!w_lo) umma_f16(acc, umma_desc_sw128(a_lo + kk * 32), bdesc, kIdesc, 1u);
+          }
+        }
+        umma_commit(&b_empty[s]);
+        if (r == 11) umma_commit(&a_empty[kh]);          // this K-half of the slab is no longer needed
+      }
+      umma_commit(&acc_full[as]);
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const int wq = warp - 4;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t accphase = (it >> 1) & 1;
+      const int w = unit / kUnitsPerWin;
+      const int t0 = (unit - w * kUnitsPerWin) * (2 * kTileM);
+      mbar_wait(&acc_full[as], accphase, p.status, 300 + as);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tile = 0; tile < 2; ++tile) {
+        const int t = t0 + tile * kTileM + wq * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256 + tile * 128;
+        __half* row = p.y_out + (static_cast<size_t>(w) * kTok + (t < kTok ? t : 0)) * kRowHalfs;
+#pragma unroll
+        for (int c32 = 0; c32 < 4; ++c32) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + c32 * 32, r);
+          tmem_wait_ld();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float v0 = lrelu(__uint_as_float(r[2 * i]) + s_bias[c32 * 32 + 2 * i]);
+            const float v1 = lrelu(__uint_as_float(r[2 * i + 1]) + s_bias[c32 * 32 + 2 * i + 1]);
+            __half h0, l0, h1, l1;
+            split_f16(v0, h0, l0);
+            split_f16(v1, h1, l1);
+            hi[i] = pack_h2(h0, h1);
+            lo[i] = pack_h2(l0, l1);
+          }
+          if (t < kTok) {
+            uint4* dh = reinterpret_cast<uint4*>(row + c32 * 32);
+            uint4* dl = reinterpret_cast<uint4*>(row + kC + c32 * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace gnm
