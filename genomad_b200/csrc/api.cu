@@ -50,6 +50,7 @@ struct gnm_handle {
   int conv_impl = 0;        // 0 tcgen05, 1 fp32 validation kernels
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
+  int conv_experiment = 0;
   // weights on device
   float* conv1_table = nullptr; float* conv1_bias = nullptr;
   __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, wv0, wv1 -- TMA stage order
@@ -315,6 +316,7 @@ static int launch_conv_tc(gnm_handle* h, int layer, int in_buf, int n, cudaStrea
   ConvTcParams p;
   p.n_tiles = n * kUnitsPerWin;                  // two-tile units
   p.status = h->status;
+  p.experiment = h->conv_experiment;
   p.bias = h->conv_bias[layer];
   p.y_out = h->ybuf[1 - in_buf];
   p.q_out = nullptr;
@@ -327,6 +329,7 @@ static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   ConvTcParams p;
   p.n_tiles = n * kTilesPerWin;
   p.status = h->status;
+  p.experiment = 0;
   p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[s];
   const int grid = std::min(h->num_sms, p.n_tiles);
   conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
@@ -542,6 +545,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   const std::string k(name);
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
+  else if (k == "conv_experiment") h->conv_experiment = value;
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;

@@ -40,6 +40,18 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 struct DeviceStatus { int code; int info0; int info1; int info2; };
 enum : int { kDevOk = 0, kDevMbarTimeout = 1 };
 
+// exactly one lane of a fully converged warp gets true (PTX elect.sync); ptxas then keeps the
+// guarded tcgen05/TMA instructions on the uniform datapath instead of a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -52,6 +52,7 @@ struct ConvTcParams {
   __half* y_out;            // [n][5997][256] or nullptr
   float* q_out;             // [n][749][128] or nullptr
   int n_tiles;              // n_windows * 47
+  int experiment;           // timing experiments only (results become wrong): 1 = no tap row shift, 2 = no epilogue stores
   DeviceStatus* status;
 };
 
@@ -119,10 +120,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
         tma_load_2d(s_b + s * kBStage, &tm_w, &b_full[s], 0, q * 128);
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (warp converged, one elected lane issues)
     uint32_t bcount = 0;
     int it = 0;
+    const uint64_t desc0 = umma_desc_sw128(0);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -146,24 +148,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant
           const int qq = q - kConvStages;
           arow = 5; w_lo = qq >> 1; kh = qq & 1; acc = acc_z; first = (qq == 0);
         }
-        const uint32_t b_addr = smem_u32(s_b + s * kBStage);
-        const uint32_t a_hi = a_base + kh * kARegion + arow * 128;
-        const uint32_t a_lo = a_base + (2 + kh) * kARegion + arow * 128;
+        if (elect_one()) {
+          const uint64_t bdesc = desc0 + (smem_u32(s_b + s * kBStage) >> 4);
+          const uint64_t ahi = desc0 + ((a_base + kh * kARegion + arow * 128) >> 4);
+          const uint64_t alo = desc0 + ((a_base + (2 + kh) * kARegion + arow * 128) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t bdesc = umma_desc_sw128(b_addr + kk * 32);
-          const uint32_t ah = a_hi + kk * 32;
-          umma_f16(acc, umma_desc_sw128(ah), bdesc, kIdesc,
-                   (first && kk == 0) ? 0u : 1u);
-          if (!w_lo) {
-            const uint32_t al = a_lo + kk * 32;
-            umma_f16(acc, umma_desc_sw128(al), bdesc, kIdesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_f16(acc, ahi + kk * 2, bdesc + kk * 2, kIdesc, (first && kk == 0) ? 0u : 1u);
+            if (!w_lo) umma_f16(acc, alo + kk * 2, bdesc + kk * 2, kIdesc, 1u);
+          }
+          umma_commit(&b_empty[s]);          // stage is free once these MMAs have read it
+          if (q == kStages - 1) {
+            umma_commit(&a_empty[ab]);       // slab is free once every MMA of the tile is done
+            umma_commit(&acc_full[ab]);      // ... and the accumulators are complete
           }
         }
-        umma_commit(&b_empty[s]);          // stage is free once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(&a_empty[ab]);           // slab is free once every MMA of the tile is done
-      umma_commit(&acc_full[ab]);          // ... and the accumulators are complete
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
@@ -340,11 +341,16 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
         tma_load_2d(s_b + s * kBStage, &tm_w, &b_full[s], 0, q * 128);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================================================================== MMA issuer
+    // The whole warp runs this loop converged; one elected lane issues.  Descriptors are built once
+    // and advanced by adding to their low word (start address >> 4), so only a couple of uniform
+    // integer ops separate consecutive tcgen05.mma instructions.
     uint32_t bcount = 0;
     int it = 0;
+    const uint64_t desc0 = umma_desc_sw128(0);
     const uint32_t a_base = smem_u32(s_a);
+    const uint32_t b_base = smem_u32(s_b);
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
@@ -358,23 +364,27 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
         const uint32_t bphase = (bcount / kNumB2Stages) & 1;
         mbar_wait(&b_full[s], bphase, p.status, 220 + s);
         tc_fence_after();
-        const uint32_t b_addr = smem_u32(s_b + s * kBStage);
+        if (elect_one()) {
+          const uint64_t bdesc = desc0 + ((b_base + s * kBStage) >> 4);
+          const int arow = (p.experiment & 1) ? 0 : tap;
+          const uint64_t ahi = desc0 + ((a_base + kh * kA2Region + arow * 128) >> 4);
+          const uint64_t alo = desc0 + ((a_base + (2 + kh) * kA2Region + arow * 128) >> 4);
+          constexpr uint32_t kTileStep = (kTileM * 128) >> 4;      // tile b starts 128 rows further down
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          const uint32_t a_hi = a_base + kh * kA2Region + (tile * kTileM + tap) * 128;
-          const uint32_t a_lo = a_base + (2 + kh) * kA2Region + (tile * kTileM + tap) * 128;
-          const uint32_t acc = acc0 + tile * 128;
+          for (int tile = 0; tile < 2; ++tile) {
+            const uint32_t acc = acc0 + tile * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bdesc = umma_desc_sw128(b_addr + kk * 32);
-            umma_f16(acc, umma_desc_sw128(a_hi + kk * 32), bdesc, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
-            if (!w_lo) umma_f16(acc, umma_desc_sw128(a_lo + kk * 32), bdesc, kIdesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(acc, ahi + tile * kTileStep + kk * 2, bdesc + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+              if (!w_lo) umma_f16(acc, alo + tile * kTileStep + kk * 2, bdesc + kk * 2, kIdesc, 1u);
+            }
           }
+          umma_commit(&b_empty[s]);
+          if (r == 11) umma_commit(&a_empty[kh]);          // this K-half of the slab is no longer needed
+          if (q == kConv2tStages - 1) umma_commit(&acc_full[as]);
         }
-        umma_commit(&b_empty[s]);
-        if (r == 11) umma_commit(&a_empty[kh]);          // this K-half of the slab is no longer needed
+        __syncwarp();
       }
-      umma_commit(&acc_full[as]);
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
@@ -408,7 +418,7 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
             hi[i] = pack_h2(h0, h1);
             lo[i] = pack_h2(l0, l1);
           }
-          if (t < kTok) {
+          if (t < kTok && !(p.experiment & 2)) {
             uint4* dh = reinterpret_cast<uint4*>(row + c32 * 32);
             uint4* dl = reinterpret_cast<uint4*>(row + kC + c32 * 32);
 #pragma unroll
