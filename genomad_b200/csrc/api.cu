@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "encode.cuh"
 #include "conv_tc.cuh"
+#include "conv_t.cuh"
 #include "conv_ref.cuh"
 #include "igloo.cuh"
 #include "dense.cuh"
@@ -51,9 +52,11 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
+  int tc_variant = 0;       // 0 = transposed N=256 kernels (production); 1 = conv2t + conv_tc<0,true> (kept for A/B timing)
+  long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv2t launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_bias = nullptr;
-  __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, wv0, wv1 -- TMA stage order
+  __half* wpack[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, wv0, wv1, wv0T, wv1T -- TMA stage order
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
@@ -74,7 +77,7 @@ struct gnm_handle {
   cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
   DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
   CUtensorMap tm_act[2];
-  CUtensorMap tm_w[4];
+  CUtensorMap tm_w[6];
   int last_n = 0;
   StageTimer timer;
   std::vector<float> stage_ms;
@@ -195,6 +198,10 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
       std::vector<__half> pk;
       pack_matrix_stages(pk, w->igloo[s].w_v);
       if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
+      std::vector<__half> pt;                              // conv_t_kernel<true>: (K-half, weight hi/lo)
+      for (int kh = 0; kh < 2; ++kh)
+        for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pt, w->igloo[s].w_v, w_lo, kh);
+      if (dev_upload(h, &h->wpack[4 + s], pt.data(), pt.size())) return 1;
     }
     if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
     if (dev_upload(h, &h->conv_bias[1], w->conv3_bias, kC)) return 1;
@@ -247,6 +254,8 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     GNM_CUDA(cudaEventCreateWithFlags(&h->in_ready[i], cudaEventDisableTiming));
     GNM_CUDA(cudaEventCreateWithFlags(&h->in_free[i], cudaEventDisableTiming));
   }
+  if (dev_alloc(h, &h->conv_dbg, static_cast<size_t>(h->num_sms) * 8)) return 1;
+  GNM_CUDA(cudaMemset(h->conv_dbg, 0, static_cast<size_t>(h->num_sms) * 8 * sizeof(long long)));
   if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
   if (dev_alloc(h, &h->h0, mb * 256)) return 1;
   if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
@@ -265,9 +274,13 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConv2tStages)) return 1;
   if (make_w_map(enc, &h->tm_w[2], h->wpack[2], 4)) return 1;
   if (make_w_map(enc, &h->tm_w[3], h->wpack[3], 4)) return 1;
+  if (make_w_map(enc, &h->tm_w[4], h->wpack[4], 4)) return 1;
+  if (make_w_map(enc, &h->tm_w[5], h->wpack[5], 4)) return 1;
 
   // ---- opt in to large dynamic shared memory
   GNM_CUDA(cudaFuncSetAttribute(conv2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2tSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
+  GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
@@ -317,23 +330,34 @@ static int launch_conv_tc(gnm_handle* h, int layer, int in_buf, int n, cudaStrea
   p.n_tiles = n * kUnitsPerWin;                  // two-tile units
   p.status = h->status;
   p.experiment = h->conv_experiment;
+  p.dbg = (h->conv_experiment & 4) ? h->conv_dbg : nullptr;
   p.bias = h->conv_bias[layer];
   p.y_out = h->ybuf[1 - in_buf];
   p.q_out = nullptr;
   const int grid = std::min(h->num_sms, p.n_tiles);
-  conv2t_kernel<<<grid, kConvThreads, kConv2tSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
-  return check_launch(h, "conv2t_kernel");
+  if (h->tc_variant == 0)
+    conv_t_kernel<false><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
+  else
+    conv2t_kernel<<<grid, kConvThreads, kConv2tSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
+  return check_launch(h, "conv kernel");
 }
 // q[s] = maxpool8(y[buf] @ w_v#s)
 static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   ConvTcParams p;
-  p.n_tiles = n * kTilesPerWin;
   p.status = h->status;
   p.experiment = 0;
+  p.dbg = nullptr;
   p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[s];
-  const int grid = std::min(h->num_sms, p.n_tiles);
-  conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
-  return check_launch(h, "conv_tc_kernel<0,true>");
+  if (h->tc_variant == 0) {
+    p.n_tiles = n * kUnitsPerWin;
+    const int grid = std::min(h->num_sms, p.n_tiles);
+    conv_t_kernel<true><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[buf], h->tm_w[4 + s], p);
+  } else {
+    p.n_tiles = n * kTilesPerWin;
+    const int grid = std::min(h->num_sms, p.n_tiles);
+    conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
+  }
+  return check_launch(h, "w_v kernel");
 }
 
 static int ensure_scratch(gnm_handle* h) {
@@ -546,6 +570,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
+  else if (k == "tc_variant") h->tc_variant = value ? 1 : 0;
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;
@@ -600,6 +625,7 @@ extern "C" int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d
   else if (k == "mpi0" || k == "mpi1") { src = h->mpi[k == "mpi1"]; count = static_cast<size_t>(n) * kPatches; }
   else if (k == "h0") { src = h->h0; count = static_cast<size_t>(n) * 256; }
   else if (k == "logits") { src = h->logits; count = static_cast<size_t>(n) * kLogitsLd; }
+  else if (k == "conv_dbg") { src = reinterpret_cast<const float*>(h->conv_dbg); count = static_cast<size_t>(h->num_sms) * 16; }
   else return fail("gnm_debug_fetch: unknown buffer " + k);
   GNM_CUDA(cudaMemcpyAsync(d_dst, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

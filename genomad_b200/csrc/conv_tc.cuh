@@ -53,6 +53,7 @@ struct ConvTcParams {
   float* q_out;             // [n][749][128] or nullptr
   int n_tiles;              // n_windows * 47
   int experiment;           // timing experiments only (results become wrong): 1 = no tap row shift, 2 = no epilogue stores
+  long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
   DeviceStatus* status;
 };
 
@@ -351,24 +352,30 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
     const uint64_t desc0 = umma_desc_sw128(0);
     const uint32_t a_base = smem_u32(s_a);
     const uint32_t b_base = smem_u32(s_b);
+    long long w_acc = 0, w_a = 0, w_b = 0, tq;
+    const long long t_begin = clock64();
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
       const uint32_t aph = it & 1;
       const uint32_t acc0 = tmem_base + as * 256;          // tile a; tile b = +128
+      tq = clock64();
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 200 + as);
+      w_acc += clock64() - tq;
       for (int q = 0; q < kConv2tStages; ++q, ++bcount) {
         const int kh = q / 12, r = q - kh * 12, tap = r >> 1, w_lo = r & 1;
-        if (r == 0) mbar_wait(&a_full[kh], aph, p.status, 210 + kh);
+        if (r == 0) { tq = clock64(); mbar_wait(&a_full[kh], aph, p.status, 210 + kh); w_a += clock64() - tq; }
         const int s = bcount % kNumB2Stages;
         const uint32_t bphase = (bcount / kNumB2Stages) & 1;
+        tq = clock64();
         mbar_wait(&b_full[s], bphase, p.status, 220 + s);
+        w_b += clock64() - tq;
         tc_fence_after();
         if (elect_one()) {
           const uint64_t bdesc = desc0 + ((b_base + s * kBStage) >> 4);
           const int arow = (p.experiment & 1) ? 0 : tap;
           const uint64_t ahi = desc0 + ((a_base + kh * kA2Region + arow * 128) >> 4);
-          const uint64_t alo = desc0 + ((a_base + (2 + kh) * kA2Region + arow * 128) >> 4);
+          const uint64_t alo = (p.experiment & 8) ? ahi : desc0 + ((a_base + (2 + kh) * kA2Region + arow * 128) >> 4);
           constexpr uint32_t kTileStep = (kTileM * 128) >> 4;      // tile b starts 128 rows further down
 #pragma unroll
           for (int tile = 0; tile < 2; ++tile) {
@@ -386,16 +393,24 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
         __syncwarp();
       }
     }
+    if (p.dbg && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = w_acc; d[2] = w_a; d[3] = w_b; d[4] = it;
+    }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int wq = warp - 4;
     int it = 0;
+    long long w_full = 0, tq;
+    const long long t_begin = clock64();
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
       const int w = unit / kUnitsPerWin;
       const int t0 = (unit - w * kUnitsPerWin) * (2 * kTileM);
+      tq = clock64();
       mbar_wait(&acc_full[as], accphase, p.status, 300 + as);
+      w_full += clock64() - tq;
       tc_fence_after();
 #pragma unroll 1
       for (int tile = 0; tile < 2; ++tile) {
@@ -432,6 +447,10 @@ conv2t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 8;
+      d[5] = clock64() - t_begin; d[6] = w_full;
     }
   }
 
