@@ -13,7 +13,6 @@
 #include "../../include/gnm.h"
 #include "common.cuh"
 #include "encode.cuh"
-#include "conv_tc.cuh"
 #include "conv_t.cuh"
 #include "conv_ref.cuh"
 #include "igloo.cuh"
@@ -52,11 +51,10 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
-  int tc_variant = 0;       // 0 = transposed N=256 kernels (production); 1 = conv2t + conv_tc<0,true> (kept for A/B timing)
-  long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv2t launch
+  long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_bias = nullptr;
-  __half* wpack[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, wv0, wv1, wv0T, wv1T -- TMA stage order
+  __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, w_v#0, w_v#1 -- TMA stage order
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
@@ -77,7 +75,7 @@ struct gnm_handle {
   cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
   DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
   CUtensorMap tm_act[2];
-  CUtensorMap tm_w[6];
+  CUtensorMap tm_w[4];
   int last_n = 0;
   StageTimer timer;
   std::vector<float> stage_ms;
@@ -147,10 +145,6 @@ static void pack_stage(std::vector<__half>& dst, const float* Wkn /* [128 k][128
       dst.push_back(w_lo ? lo : hi);
     }
 }
-static void pack_matrix_stages(std::vector<__half>& dst, const float* Wkn) {   // order: (hi,k0) (hi,k1) (lo,k0) (lo,k1)
-  for (int w_lo = 0; w_lo < 2; ++w_lo)
-    for (int kh = 0; kh < 2; ++kh) pack_stage(dst, Wkn, w_lo, kh);
-}
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_handle** out) {
@@ -182,26 +176,23 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (dev_upload(h, &h->conv1_table, w->conv1_kernel, static_cast<size_t>(kTaps) * kVocab * kC)) return 1;
   if (dev_upload(h, &h->conv1_bias, w->conv1_bias, kC)) return 1;
 
-  // ---- tensor-core weight packs, in the order the kernels consume their 16 KB stages
+  // ---- tensor-core weight packs, in the order conv_t_kernel consumes its 16 KB stages
   {
     const float* convw[2] = {w->conv2_kernel, w->conv3_kernel};
     for (int L = 0; L < 2; ++L) {
-      std::vector<__half> pk;                              // conv2t_kernel: (K-half, tap, weight hi/lo)
-      pk.reserve(static_cast<size_t>(kConv2tStages) * 128 * 64);
+      std::vector<__half> pk;                              // conv: (K-half, tap, weight hi/lo)
+      pk.reserve(static_cast<size_t>(kConvStages) * 128 * 64);
       for (int kh = 0; kh < 2; ++kh)
         for (int tap = 0; tap < kTaps; ++tap)
           for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, w_lo, kh);
       if (dev_upload(h, &h->wpack[L], pk.data(), pk.size())) return 1;
       if (dev_upload(h, &h->conv_w32[L], convw[L], static_cast<size_t>(kTaps) * kC * kC)) return 1;
     }
-    for (int s = 0; s < 2; ++s) {                          // conv_tc_kernel<0,true>: (hi,k0) (hi,k1) (lo,k0) (lo,k1)
+    for (int s = 0; s < 2; ++s) {                          // w_v: (K-half, weight hi/lo)
       std::vector<__half> pk;
-      pack_matrix_stages(pk, w->igloo[s].w_v);
-      if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
-      std::vector<__half> pt;                              // conv_t_kernel<true>: (K-half, weight hi/lo)
       for (int kh = 0; kh < 2; ++kh)
-        for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pt, w->igloo[s].w_v, w_lo, kh);
-      if (dev_upload(h, &h->wpack[4 + s], pt.data(), pt.size())) return 1;
+        for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pk, w->igloo[s].w_v, w_lo, kh);
+      if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
     }
     if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
     if (dev_upload(h, &h->conv_bias[1], w->conv3_bias, kC)) return 1;
@@ -270,18 +261,14 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (get_encode_fn(&enc)) return 1;
   for (int i = 0; i < 2; ++i)
     if (make_act_map(enc, &h->tm_act[i], h->ybuf[i], max_batch)) return 1;
-  if (make_w_map(enc, &h->tm_w[0], h->wpack[0], kConv2tStages)) return 1;
-  if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConv2tStages)) return 1;
-  if (make_w_map(enc, &h->tm_w[2], h->wpack[2], 4)) return 1;
-  if (make_w_map(enc, &h->tm_w[3], h->wpack[3], 4)) return 1;
-  if (make_w_map(enc, &h->tm_w[4], h->wpack[4], 4)) return 1;
-  if (make_w_map(enc, &h->tm_w[5], h->wpack[5], 4)) return 1;
+  if (make_w_map(enc, &h->tm_w[0], h->wpack[0], kConvStages)) return 1;
+  if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConvStages)) return 1;
+  if (make_w_map(enc, &h->tm_w[2], h->wpack[2], kWvStages)) return 1;
+  if (make_w_map(enc, &h->tm_w[3], h->wpack[3], kWvStages)) return 1;
 
   // ---- opt in to large dynamic shared memory
-  GNM_CUDA(cudaFuncSetAttribute(conv2t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2tSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
-  GNM_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
   GNM_CUDA(cudaFuncSetAttribute(patch_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
@@ -325,9 +312,9 @@ static void timer_mark(gnm_handle* h, const char* name, cudaStream_t st) {
 }
 
 // layer 0: conv2 (y[in] -> y[1-in]); layer 1: conv3
-static int launch_conv_tc(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t st) {
+static int launch_conv(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t st) {
   ConvTcParams p;
-  p.n_tiles = n * kUnitsPerWin;                  // two-tile units
+  p.n_tiles = n * kUnitsPerWin;                  // 256-position units
   p.status = h->status;
   p.experiment = h->conv_experiment;
   p.dbg = (h->conv_experiment & 4) ? h->conv_dbg : nullptr;
@@ -335,11 +322,8 @@ static int launch_conv_tc(gnm_handle* h, int layer, int in_buf, int n, cudaStrea
   p.y_out = h->ybuf[1 - in_buf];
   p.q_out = nullptr;
   const int grid = std::min(h->num_sms, p.n_tiles);
-  if (h->tc_variant == 0)
-    conv_t_kernel<false><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
-  else
-    conv2t_kernel<<<grid, kConvThreads, kConv2tSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
-  return check_launch(h, "conv kernel");
+  conv_t_kernel<false><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
+  return check_launch(h, "conv_t_kernel<false>");
 }
 // q[s] = maxpool8(y[buf] @ w_v#s)
 static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
@@ -348,16 +332,10 @@ static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   p.experiment = 0;
   p.dbg = nullptr;
   p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[s];
-  if (h->tc_variant == 0) {
-    p.n_tiles = n * kUnitsPerWin;
-    const int grid = std::min(h->num_sms, p.n_tiles);
-    conv_t_kernel<true><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[buf], h->tm_w[4 + s], p);
-  } else {
-    p.n_tiles = n * kTilesPerWin;
-    const int grid = std::min(h->num_sms, p.n_tiles);
-    conv_tc_kernel<0, true><<<grid, kConvThreads, kConvSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
-  }
-  return check_launch(h, "w_v kernel");
+  p.n_tiles = n * kUnitsPerWin;
+  const int grid = std::min(h->num_sms, p.n_tiles);
+  conv_t_kernel<true><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
+  return check_launch(h, "conv_t_kernel<true>");
 }
 
 static int ensure_scratch(gnm_handle* h) {
@@ -423,10 +401,10 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     timer_mark(h, "wv0", st);
     if (launch_wv_tc(h, 0, 0, n, st)) return 1;               // y1 (buf0) -> q0
     timer_mark(h, "conv2", st);
-    if (launch_conv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1)
+    if (launch_conv(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1)
     if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
     timer_mark(h, "conv3", st);
-    if (launch_conv_tc(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
+    if (launch_conv(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
     if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
     timer_mark(h, "wv1", st);
     if (launch_wv_tc(h, 1, 0, n, st)) return 1;               // y3 (buf0) -> q1
@@ -570,7 +548,6 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
-  else if (k == "tc_variant") h->tc_variant = value ? 1 : 0;
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;

@@ -1,36 +1,81 @@
-// K2/K3 (production): causal Conv1D(128->128, k=6) + LeakyReLU and the IGLOO value projection
-// (y @ w_v, MaxPool1D(8)) on tcgen05, "transposed" formulation.
+// K2/K3: causal Conv1D(128->128, k=6) + LeakyReLU, and the IGLOO value projection (y @ w_v, MaxPool1D(8)),
+// as ONE persistent tcgen05 kernel template (conv_t_kernel<false> / conv_t_kernel<true>).
 //
-// Reference semantics: genomad/neural_network/igloo.py:64-72 (conv + LeakyReLU(0.1)), :208-210 (w_v, max-pool);
-// arithmetic recipe (fp16 hi/lo 3-pass split, fp32 accumulation in TMEM): see conv_tc.cuh.
+// Reference semantics:
+//   Conv1D x2 + LeakyReLU(0.1)      genomad/neural_network/igloo.py:64-72
+//         y'[t,:] = lrelu(b + sum_{j=0..5, t-5+j>=0} y[t-5+j,:] @ W[j])      W: [6][128 in][128 out]
+//   y_proj = y @ w_v, MaxPool1D(8)  genomad/neural_network/igloo.py:208-210
+//         q[g,:] = max_{r<8} (y[8g+r,:] @ Wv)     g < 749 (positions 5992..5996 are dropped)
 //
-// Why transposed.  Measured on B200 (tools/mma_microbench.cu, profiles/r01_mma_microbench.md):
-// a cta_group::1 M=128 x N=128 x K=16 UMMA needs 128 B/cycle of shared-memory operand bandwidth --
-// all of it -- and in the real kernel (TMA fills + epilogue traffic sharing the same banks) it ran
-// at ~109 instead of 64 cycles; the N=256 shape needs 96 B/cycle and ran at 100 % in every test.
-// The model only has 128 output channels, so N=256 is obtained by swapping the operand roles:
+// Arithmetic: fp32-equivalent "3-pass split".  Every fp32 operand x is carried as two fp16 numbers
+// hi = fp16(x), lo = fp16(x - hi) (|x - hi - lo| <~ 2^-22 |x|).  A product A*B is evaluated on the
+// tensor cores as Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32 accumulation in TMEM (the dropped Alo*Blo
+// term is ~2^-22).  tools/precision_study.py (profiles/r01_precision_study.md) shows why a single
+// TF32/fp16 pass is not enough for the 1e-4 parity bar (1.4e-4 worst case for the convs, 7e-4 for w_v)
+// while this recipe gives ~7e-6.
+//
+// Data layout.  Activations are [n][5997][256] fp16 (128 "hi" | 128 "lo" halves per 512-byte row).
+// One work unit = 256 consecutive positions of one window (24 units per window).  For each
+// (plane, K-half) two TMA boxes of 136 rows x 64 channels bring rows t0-5 .. t0+266 of the window into
+// a 272-row SWIZZLE_128B slab ONCE; conv tap j is the same slab read j rows further down -- only the
+// UMMA descriptor start address changes (row j is position t0-5+j; TMA zero-fills rows with t < 0 or
+// t >= 5997, which is exactly Keras' causal padding).  Measured on B200 (profiles/r01_bringup.md): the
+// 128B swizzle is a function of the absolute shared-memory address, so a descriptor may start at any
+// 128-byte row of a 1024B-aligned slab with base_offset = 0.
+//
+// Operand roles ("transposed" formulation).  Measured (tools/mma_microbench.cu,
+// profiles/r01_mma_microbench.md): a cta_group::1 M=128 x N=128 x K=16 UMMA needs 128 B/cycle of
+// shared-memory operand bandwidth -- all of it -- and in the real kernel (TMA fills and epilogue
+// traffic share the banks) ran at ~109 instead of 64 cycles; N=256 needs 96 B/cycle.  The model has
+// only 128 output channels, so N=256 comes from swapping the roles:
 //
 //     D^T[cout (M=128 TMEM lanes)][position (N=256 TMEM columns)] += W_tap^T[cout][cin] * Y[position + tap][cin]
 //
-//   A operand = one 16 KB weight stage  [128 cout][64 cin]  fp16 K-major SWIZZLE_128B (streamed by TMA),
-//   B operand = 256 consecutive rows of the activation slab [272 rows][64 cin] (the tap is a row offset
-//               of the descriptor start address, exactly as before), one work unit = 2 adjacent tiles.
+//   A operand = one 16 KB weight stage [128 cout][64 cin] fp16 K-major SWIZZLE_128B (streamed by TMA through
+//               a 4-stage ring, host-packed in consumption order), shared by both tiles of the unit;
+//   B operand = 256 consecutive rows of the activation slab.
 //
-// Schedule (unchanged from conv2t): stages ordered K-half-major so each half of the slab is reloaded for
-// the next unit while the other half is still in use; separate activation / weight producer threads;
-// 2 accumulator sets x 256 TMEM columns so the epilogue of unit u overlaps the MMAs of unit u+1.
+// Schedule.  Stages are ordered K-half-major (all taps of channels 0..63, then 64..127) so each half of
+// the slab is free after 12 stages and is reloaded for the NEXT unit while the other half is in use;
+// activations and weights have separate producer threads; 2 accumulator sets x 256 TMEM columns let the
+// epilogue of unit u overlap the MMAs of unit u+1.  The MMA warp stays converged and issues through
+// elect.sync so consecutive tcgen05.mma stay on the uniform datapath (the first version issued from a
+// divergent single lane and spent ~140 cycles per MMA in the compiler's waterfall loop).
 //
-// Epilogue: a thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
-//   conv : bias + LeakyReLU + fp16 hi/lo split, transposed through a 16 KB shared staging tile
-//          ([32 positions][256 halves]) and written back as full 512-byte activation rows;
-//   w_v  : max over 8 consecutive positions is a max over 8 registers (no shuffles); a warp writes
-//          128 contiguous bytes of q[g][:] per pooled row.
+// Warp roles (256 threads, 1 CTA per SM, persistent over units):
+//   warp 0 lane 0 : weight producer (TMA)          warp 3 lane 0 : activation producer (TMA)
+//   warp 1        : tcgen05.mma issuer             warp 2        : TMEM allocator
+//   warps 4..7    : epilogue.  A thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
+//       conv : bias + LeakyReLU + fp16 hi/lo split, transposed through a 16 KB shared staging tile
+//              ([32 positions][256 halves]) and written back as full 512-byte activation rows;
+//       w_v  : the max over 8 consecutive positions is a max over 8 registers (no shuffles); a warp writes
+//              128 contiguous bytes of q[g][:] per pooled row.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
-#include "conv_tc.cuh"
 
 namespace gnm {
+
+constexpr int kTileM       = 128;
+constexpr int kUnitsPerWin = (kTok + 2 * kTileM - 1) / (2 * kTileM);   // 24
+constexpr int kSlabRows    = 136;                                // rows per TMA box
+constexpr int kARegion     = kSlabRows * 128;                    // bytes per box: rows x 128 B (64 fp16)  = 17408
+constexpr int kA2Region    = 2 * kARegion;                       // 272-row slab region                    = 34816
+constexpr int kA2Bytes     = 4 * kA2Region;                      // hi.k0 hi.k1 lo.k0 lo.k1                = 139264
+constexpr int kBStage      = 128 * 128;                          // one weight stage: 128 rows x 64 fp16   = 16384
+constexpr int kConvThreads = 256;
+constexpr int kConvStages  = 24;                                 // conv: (K-half, tap, weight hi/lo)
+constexpr int kWvStages    = 4;                                  // w_v : (K-half, weight hi/lo)
+
+struct ConvTcParams {
+  const float* bias;        // [128] (conv) or nullptr (w_v)
+  __half* y_out;            // [n][5997][256] (conv) or nullptr
+  float* q_out;             // [n][749][128] (w_v) or nullptr
+  int n_tiles;              // number of work units = n_windows * 24
+  int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores
+  long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
+  DeviceStatus* status;
+};
 
 constexpr int kTWStages   = 4;                                   // weight ring depth (16 KB each)
 constexpr int kTStageTile = 32 * kRowHalfs * 2;                  // 16 KB epilogue staging tile

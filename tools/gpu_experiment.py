@@ -12,9 +12,7 @@ n = 1024
 clf = engine.Classifier(None, device=0, max_batch=n)
 a = torch.from_numpy(make_windows(n)).cuda()
 out = torch.empty((n, 3), dtype=torch.float32, device="cuda")
-import os
-clf.set_option("tc_variant", int(os.environ.get("TC_VARIANT", "0")))
-for exp in [int(x) for x in (sys.argv[1:] or ["0", "1", "2", "3"])]:
+for exp in [int(x) for x in (sys.argv[1:] or ["0", "2"])]:
     # experiment 8: A "lo" operand replaced by the "hi" plane (normal fp16 numbers instead of subnormals)
     clf.set_option("conv_experiment", exp)
     for _ in range(2):
@@ -34,6 +32,6 @@ clf.set_option("conv_experiment", 4)
 clf.predict_ascii(a, out); torch.cuda.synchronize()
 d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
 names = ["mma_total", "mma_wait_acc_empty", "mma_wait_a_full", "mma_wait_b_full", "units", "epi_total", "epi_wait_acc_full"]
-print("conv2t cycle breakdown (mean over CTAs, last conv launch = conv3):")
+print("conv_t cycle breakdown (mean over CTAs, last conv launch = conv3):")
 for i, nm in enumerate(names):
     print(f"   {nm:22s} {d[:, i].mean():12.0f}  (per unit {d[:, i].mean() / max(d[:, 4].mean(), 1):9.0f})")
