@@ -53,7 +53,7 @@ struct gnm_handle {
   int conv_experiment = 0;
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
-  float* conv1_table = nullptr; float* conv1_bias = nullptr;
+  float* conv1_table = nullptr; float* conv1_triple = nullptr; float* conv1_bias = nullptr;
   __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, w_v#0, w_v#1 -- TMA stage order
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
@@ -175,6 +175,21 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- first layer table + bias
   if (dev_upload(h, &h->conv1_table, w->conv1_kernel, static_cast<size_t>(kTaps) * kVocab * kC)) return 1;
   if (dev_upload(h, &h->conv1_bias, w->conv1_bias, kC)) return 1;
+  {
+    // "triple" tables of layer 1 (encode.cuh): A[code] = (W1[0][k0] + W1[1][k1]) + W1[2][k2] for the three 4-mers of a
+    // 6-base word, B likewise with taps 3..5 -- same fp32 operation order as the kernel's fallback path.
+    std::vector<float> tri(static_cast<size_t>(2) * kTriple * kC);
+    for (int half = 0; half < 2; ++half)
+      for (int code = 0; code < kTriple; ++code) {
+        const int k0 = 1 + (code >> 4), k1 = 1 + ((code >> 2) & 255), k2 = 1 + (code & 255);
+        const float* r0 = w->conv1_kernel + (static_cast<size_t>(3 * half + 0) * kVocab + k0) * kC;
+        const float* r1 = w->conv1_kernel + (static_cast<size_t>(3 * half + 1) * kVocab + k1) * kC;
+        const float* r2 = w->conv1_kernel + (static_cast<size_t>(3 * half + 2) * kVocab + k2) * kC;
+        float* dst = tri.data() + (static_cast<size_t>(half) * kTriple + code) * kC;
+        for (int c = 0; c < kC; ++c) dst[c] = (r0[c] + r1[c]) + r2[c];
+      }
+    if (dev_upload(h, &h->conv1_triple, tri.data(), tri.size())) return 1;
+  }
 
   // ---- tensor-core weight packs, in the order conv_t_kernel consumes its 16 KB stages
   {
@@ -366,8 +381,8 @@ static int launch_wv_ref(gnm_handle* h, int s, int in_buf, int n, cudaStream_t s
 }
 
 static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
-  // enough window chunks to give every SM a few CTAs, while each CTA amortises its 64 KB weight stage
-  int chunks = std::max(1, std::min(n, (4 * h->num_sms + kGatherGroups - 1) / kGatherGroups));
+  // one resident wave: 148 patch groups x 5 window chunks = 740 CTAs = 5 per SM (32 KB smem, 128 threads each)
+  int chunks = std::max(1, std::min(n, 5 * h->num_sms / kGatherGroups));
   const int wpc = (n + chunks - 1) / chunks;
   chunks = (n + wpc - 1) / wpc;
   dim3 grid(kGatherGroups, chunks);
@@ -378,8 +393,14 @@ static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) 
 
 static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
                         int K, const float* bias, const float* scale, const float* shift, int relu, cudaStream_t st) {
-  dim3 grid((N + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
-  sgemm_epi_kernel<<<grid, kGemmThreads, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+  const int nb = (N + kGemmBN - 1) / kGemmBN;
+  if (nb * ((M + 63) / 64) >= 4 * h->num_sms) {           // enough 64-row tiles to fill the chip
+    dim3 grid(nb, (M + 63) / 64);
+    sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+  } else {
+    dim3 grid(nb, (M + 31) / 32);
+    sgemm_epi_kernel<32><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+  }
   return check_launch(h, "sgemm_epi_kernel");
 }
 
@@ -390,9 +411,9 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   timer_mark(h, "embed_conv1", st);
   if (d_ascii)
-    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_bias, h->ybuf[0], n);
+    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
   else
-    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_bias, h->ybuf[0], n);
+    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
   if (check_launch(h, "embed_conv1_kernel")) return 1;
   timer_mark(h, "gather0", st);
   if (launch_gather(h, 0, 0, n, st)) return 1;

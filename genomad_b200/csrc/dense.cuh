@@ -13,19 +13,24 @@ namespace gnm {
 
 // ------------------------------------------------------------------------------------------
 // C[M][ldc] = epi(A[M][K] @ B[K][N]) in fp32 on the CUDA cores (these GEMMs are < 0.3 % of the
-// model's FLOPs).  64x64 tile, 16-deep K slices, 256 threads x (4x4) outputs, guards on every edge.
+// model's FLOPs).  16-deep K slices, (4x4) outputs per thread, guards on every edge.  Each output element
+// is accumulated in k order by one thread, so results do not depend on the tile shape or batch position.
 // epi: v = acc + bias[n]; if scale: v = v * scale[n] + shift[n]; if relu: v = max(v, 0).
 // ------------------------------------------------------------------------------------------
-constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
+constexpr int kGemmBN = 64, kGemmBK = 16;
 
-__global__ void __launch_bounds__(kGemmThreads)
+// kBM x 64 output tile per CTA (kBM = 32 or 64; kBM*4 threads, 4x4 outputs each).  The 32-row variant is used when
+// the 64-row grid would leave SMs idle (M = 1024 windows -> only 192 CTAs for the logits GEMM).
+template <int kBM>
+__global__ void __launch_bounds__(kBM * 4)
 sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const float* __restrict__ shift, int relu) {
-  __shared__ float s_a[kGemmBK][kGemmBM + 4];
+  constexpr int kThreads = kBM * 4;
+  __shared__ float s_a[kGemmBK][kBM + 4];
   __shared__ float s_b[kGemmBK][kGemmBN + 4];
-  const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kGemmBN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -33,8 +38,7 @@ sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kGemmBK) {
-    // A tile: 64 rows x 16 k  (thread -> row = tid/4, 4 consecutive k)
-    {
+    {   // A tile: kBM rows x 16 k  (thread -> row = tid/4, 4 consecutive k)
       const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) * 4;
       const int gm = m0 + r;
 #pragma unroll
@@ -43,9 +47,9 @@ sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__
         s_a[kk + i][r] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
       }
     }
-    // B tile: 16 k x 64 cols (thread -> k = tid/16, 4 consecutive cols)
-    {
-      const int kk = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
+    // B tile: 16 k x 64 cols, 4 consecutive cols per slot
+    for (int slot = threadIdx.x; slot < kGemmBK * kGemmBN / 4; slot += kThreads) {
+      const int kk = slot >> 4, c = (slot & 15) * 4;
       const int gk = k0 + kk;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

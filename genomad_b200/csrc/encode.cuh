@@ -67,18 +67,27 @@ encode_tokens_kernel(const uint8_t* __restrict__ ascii, uint16_t* __restrict__ t
 
 // ------------------------------------------------------------------------------------------
 // K0+K1 fused: one CTA per (window, 256-position segment).  Tokens are computed into shared
-// memory (from ASCII, or copied from a token buffer), then one warp per position sums the six
-// 512-byte rows of the [6][257][128] table (L2-resident, 789 KB), adds the bias, applies
-// LeakyReLU and writes the activation row as fp16 hi | fp16 lo (256 halves = 512 B).
-// Taps are added in the fixed order j = 0..5 so results do not depend on scheduling.
+// memory (from ASCII, or copied from a token buffer), then one warp per position produces the
+// 128-channel activation row and writes it as fp16 hi | fp16 lo (256 halves = 512 B).
+//
+//   y1[t] = lrelu( (A + B) + bias ),   A = (W1[0][k0] + W1[1][k1]) + W1[2][k2],  B = (W1[3][k3] + W1[4][k4]) + W1[5][k5]
+//
+// with k_j = tok[t-5+j] and padded taps contributing exactly 0.  Tokens t-5, t-4, t-3 are the 4-mers
+// of 6 consecutive bases, so A has only 4^6 = 4096 possible values when those bases are all ACGT, and
+// likewise B: two 2 MB "triple" tables (built on the host with the same fp32 operation order, so a
+// table hit is bit-identical to the three-row sum) replace six 512-byte row reads by two.  Positions
+// next to the window start, or touching a non-ACGT base, fall back to the single-row table.  The first
+// version (six reads per position) was L1-bandwidth bound: l1tex 97 % busy (profiles/r01_small_kernels_ncu.md).
 // ------------------------------------------------------------------------------------------
 constexpr int kEmbSeg = 256;
 constexpr int kEmbThreads = 256;
+constexpr int kTriple = 4096;
 
 template <bool kFromAscii>
 __global__ void __launch_bounds__(kEmbThreads)
 embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict__ tokens_in,
                    const float* __restrict__ table,   // [6][257][128]
+                   const float* __restrict__ triple,  // [2][4096][128]: A-table, B-table
                    const float* __restrict__ bias,    // [128]
                    __half* __restrict__ y_out,        // [n][5997][256]
                    int n_windows) {
@@ -112,25 +121,37 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 b4 = reinterpret_cast<const float4*>(bias)[lane];
   const float4* tab4 = reinterpret_cast<const float4*>(table);
+  const float4* tri4 = reinterpret_cast<const float4*>(triple);
+  auto row = [&](int j, int tk) -> float4 {
+    return tk >= 0 ? __ldg(tab4 + (static_cast<size_t>(j) * kVocab + tk) * (kC / 4) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto add4 = [](float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
   for (int i = warp; i < kEmbSeg; i += kEmbThreads / 32) {
     const int t = t0 + i;
     if (t >= kTok) break;
-    float4 v[kTaps];
+    int tk[kTaps];
 #pragma unroll
-    for (int j = 0; j < kTaps; ++j) {
-      const int tk = s_tok[i + j];                   // position t - 5 + j
-      v[j] = tk >= 0 ? __ldg(tab4 + (static_cast<size_t>(j) * kVocab + tk) * (kC / 4) + lane)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kTaps; ++j) tk[j] = s_tok[i + j];          // token at position t - 5 + j
+    float4 A, B;
+    if (tk[0] > 0 && tk[2] > 0) {                                   // bases t-5 .. t all ACGT (implies tk[1] > 0)
+      const int code = ((tk[0] - 1) << 4) | ((tk[2] - 1) & 15);
+      A = __ldg(tri4 + static_cast<size_t>(code) * (kC / 4) + lane);
+    } else {
+      A = add4(add4(row(0, tk[0]), row(1, tk[1])), row(2, tk[2]));
     }
-    float4 a = v[0];
-#pragma unroll
-    for (int j = 1; j < kTaps; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    if (tk[3] > 0 && tk[5] > 0) {                                   // bases t-2 .. t+3 all ACGT (implies tk[4] > 0)
+      const int code = ((tk[3] - 1) << 4) | ((tk[5] - 1) & 15);
+      B = __ldg(tri4 + (static_cast<size_t>(kTriple) + code) * (kC / 4) + lane);
+    } else {
+      B = add4(add4(row(3, tk[3]), row(4, tk[4])), row(5, tk[5]));
+    }
+    float4 a = add4(A, B);
     a.x = lrelu(a.x + b4.x); a.y = lrelu(a.y + b4.y); a.z = lrelu(a.z + b4.z); a.w = lrelu(a.w + b4.w);
     __half h0, h1, h2, h3, l0, l1, l2, l3;
     split_f16(a.x, h0, l0); split_f16(a.y, h1, l1); split_f16(a.z, h2, l2); split_f16(a.w, h3, l3);
-    __half* row = y_out + (static_cast<size_t>(w) * kTok + t) * kRowHalfs;
-    *reinterpret_cast<uint2*>(row + lane * 4) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-    *reinterpret_cast<uint2*>(row + kC + lane * 4) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+    __half* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowHalfs;
+    *reinterpret_cast<uint2*>(rowp + lane * 4) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+    *reinterpret_cast<uint2*>(rowp + kC + lane * 4) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
   }
 }
 

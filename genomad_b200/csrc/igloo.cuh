@@ -13,17 +13,22 @@
 namespace gnm {
 
 // ------------------------------------------------------------------------------------------
-// Patch gather.  CTA = (32-patch group, window chunk).  The group's folded weights
-// (32 x 4 x 128 fp32 = 64 KB) are staged in shared memory once and reused for every window
-// of the chunk; each warp owns 4 patches and, per window, issues its 16 row loads (one
-// 512-byte activation row = 16 B per lane: 4 fp16 hi + 4 fp16 lo) back to back, multiplies
-// by the staged weights and reduces over the 128 channels with warp shuffles.
-// HBM-bound: 8400 rows x 512 B = 4.3 MB of activation rows per window per IGLOO kernel.
+// Patch gather.  Grid = (148 patch groups of <=15 patches) x (window chunks), sized by the host to
+// exactly one resident wave (5 CTAs of 128 threads per SM).  A CTA stages its group's folded weights
+// (<= 16 x 4 x 128 fp32 = 32 KB) in shared memory once and reuses them for every window of its chunk.
+// Each warp owns 4 patches = 16 activation rows per window: it issues all 16 row loads back to back
+// (one 512-byte row = ONE 16-byte load per lane: lanes 0-15 fetch the fp16 "hi" half-row, lanes 16-31
+// the "lo" half-row), multiplies by the staged weights (lanes l and l+16 use the same 8 weights, so
+// hi*w and lo*w are summed by the final warp-shuffle reduction) and writes 4 scores.
+// All groups walk the windows in the same order, so the ~1.9x re-use of popular rows hits in L2.
+// HBM-bound: 8400 rows x 512 B = 4.3 MB of activation rows per window per IGLOO kernel (2.4 MB distinct).
 // ------------------------------------------------------------------------------------------
-constexpr int kGatherPB = 32;                                    // patches per CTA
-constexpr int kGatherThreads = 256;
-constexpr int kGatherGroups = (kPatches + kGatherPB - 1) / kGatherPB;   // 66
+constexpr int kGatherGroups = 148;
+constexpr int kGatherPB = 16;                                    // patch slots per CTA (4 warps x 4)
+constexpr int kGatherPPG = (kPatches + kGatherGroups - 1) / kGatherGroups;   // 15 patches per group
+constexpr int kGatherThreads = 128;
 constexpr int kGatherSmem = kGatherPB * kPatchLen * kC * 4 + kGatherPB * kPatchLen * 4 + kGatherPB * 4;
+static_assert(kGatherPPG <= kGatherPB, "patch group does not fit the CTA");
 
 __global__ void __launch_bounds__(kGatherThreads)
 patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
@@ -33,11 +38,11 @@ patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
                     float* __restrict__ mpi,              // [n][2100]
                     int n_windows, int windows_per_cta) {
   extern __shared__ __align__(16) uint8_t s_g[];
-  float* s_wf = reinterpret_cast<float*>(s_g);                                    // [32][4][128]
-  int* s_idx = reinterpret_cast<int*>(s_wf + kGatherPB * kPatchLen * kC);          // [32][4]
-  float* s_bias = reinterpret_cast<float*>(s_idx + kGatherPB * kPatchLen);         // [32]
-  const int p0 = blockIdx.x * kGatherPB;
-  const int np = min(kGatherPB, kPatches - p0);
+  float* s_wf = reinterpret_cast<float*>(s_g);                                    // [16][4][128]
+  int* s_idx = reinterpret_cast<int*>(s_wf + kGatherPB * kPatchLen * kC);          // [16][4]
+  float* s_bias = reinterpret_cast<float*>(s_idx + kGatherPB * kPatchLen);         // [16]
+  const int p0 = blockIdx.x * kGatherPPG;
+  const int np = max(0, min(kGatherPPG, kPatches - p0));
   for (int i = threadIdx.x; i < kGatherPB * kPatchLen * kC / 4; i += kGatherThreads) {
     const int pp = i / (kPatchLen * kC / 4);
     reinterpret_cast<float4*>(s_wf)[i] = pp < np
@@ -50,34 +55,33 @@ patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;               // half 0: "hi" plane, 1: "lo" plane
+  int rowoff[16];                                            // byte offset of this lane's 16 B inside each of the 16 rows
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    rowoff[j] = s_idx[warp * 16 + j] * (kRowHalfs * 2) + half * (kC * 2) + l16 * 16;
+  const float* wl = s_wf + warp * 16 * kC + l16 * 8;          // this lane's 8 weights of row j: wl[j*128 .. +7]
   const int w_begin = blockIdx.y * windows_per_cta;
   const int w_end = min(n_windows, w_begin + windows_per_cta);
   for (int w = w_begin; w < w_end; ++w) {
-    const __half* yw = y + static_cast<size_t>(w) * kTok * kRowHalfs;
-    uint2 hi[4][4], lo[4][4];
+    const uint8_t* yw = reinterpret_cast<const uint8_t*>(y) + static_cast<size_t>(w) * kTok * (kRowHalfs * 2);
+    uint4 v[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __half* row = yw + static_cast<size_t>(s_idx[(warp * 4 + i) * 4 + k]) * kRowHalfs;
-        hi[i][k] = __ldg(reinterpret_cast<const uint2*>(row) + lane);
-        lo[i][k] = __ldg(reinterpret_cast<const uint2*>(row + kC) + lane);
-      }
+    for (int j = 0; j < 16; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(yw + rowoff[j]));
     float acc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float a = 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 wv = *reinterpret_cast<const float4*>(s_wf + ((warp * 4 + i) * 4 + k) * kC + lane * 4);
-        const __half2 h01 = *reinterpret_cast<const __half2*>(&hi[i][k].x);
-        const __half2 h23 = *reinterpret_cast<const __half2*>(&hi[i][k].y);
-        const __half2 l01 = *reinterpret_cast<const __half2*>(&lo[i][k].x);
-        const __half2 l23 = *reinterpret_cast<const __half2*>(&lo[i][k].y);
-        a = fmaf(__low2float(h01) + __low2float(l01), wv.x, a);
-        a = fmaf(__high2float(h01) + __high2float(l01), wv.y, a);
-        a = fmaf(__low2float(h23) + __low2float(l23), wv.z, a);
-        a = fmaf(__high2float(h23) + __high2float(l23), wv.w, a);
+        const int j = i * 4 + k;
+        const float4 w0 = *reinterpret_cast<const float4*>(wl + j * kC);
+        const float4 w1 = *reinterpret_cast<const float4*>(wl + j * kC + 4);
+        const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
+        a = fmaf(__low2float(h[0]), w0.x, a); a = fmaf(__high2float(h[0]), w0.y, a);
+        a = fmaf(__low2float(h[1]), w0.z, a); a = fmaf(__high2float(h[1]), w0.w, a);
+        a = fmaf(__low2float(h[2]), w1.x, a); a = fmaf(__high2float(h[2]), w1.y, a);
+        a = fmaf(__low2float(h[3]), w1.z, a); a = fmaf(__high2float(h[3]), w1.w, a);
       }
       acc[i] = a;
     }
@@ -88,8 +92,8 @@ patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
     if (lane < 4) {
       const int pl = warp * 4 + lane;
       if (pl < np) {
-        const float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        mpi[static_cast<size_t>(w) * kPatches + p0 + pl] = v + s_bias[pl];
+        const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        mpi[static_cast<size_t>(w) * kPatches + p0 + pl] = r + s_bias[pl];
       }
     }
   }
