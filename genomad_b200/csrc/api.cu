@@ -51,6 +51,7 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
+  int gather_cta_per_sm = 2;          // patch_gather_kernel keeps its weights in registers (240 regs): 2 CTAs of 128 threads per SM
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_triple = nullptr; float* conv1_bias = nullptr;
@@ -381,8 +382,8 @@ static int launch_wv_ref(gnm_handle* h, int s, int in_buf, int n, cudaStream_t s
 }
 
 static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
-  // one resident wave: 148 patch groups x 5 window chunks = 740 CTAs = 5 per SM (32 KB smem, 128 threads each)
-  int chunks = std::max(1, std::min(n, 5 * h->num_sms / kGatherGroups));
+  // one resident wave: 148 patch groups x window chunks, gather_cta_per_sm CTAs per SM (33 KB smem, 128 threads each)
+  int chunks = std::max(1, std::min(n, h->gather_cta_per_sm * h->num_sms / kGatherGroups));
   const int wpc = (n + chunks - 1) / chunks;
   chunks = (n + wpc - 1) / wpc;
   dim3 grid(kGatherGroups, chunks);
@@ -394,7 +395,7 @@ static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) 
 static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
                         int K, const float* bias, const float* scale, const float* shift, int relu, cudaStream_t st) {
   const int nb = (N + kGemmBN - 1) / kGemmBN;
-  if (nb * ((M + 63) / 64) >= 4 * h->num_sms) {           // enough 64-row tiles to fill the chip
+  if (M >= 64) {                                           // 32-row tiles only for tiny batches (measured slower otherwise)
     dim3 grid(nb, (M + 63) / 64);
     sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
   } else {
@@ -569,6 +570,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
+  else if (k == "gather_cta_per_sm") h->gather_cta_per_sm = std::max(1, value);
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;

@@ -14,11 +14,11 @@ namespace gnm {
 
 // ------------------------------------------------------------------------------------------
 // Patch gather.  Grid = (148 patch groups of <=15 patches) x (window chunks), sized by the host to
-// exactly one resident wave (5 CTAs of 128 threads per SM).  A CTA stages its group's folded weights
+// exactly one resident wave (CTAs of 128 threads, several per SM).  A CTA stages its group's folded weights
 // (<= 16 x 4 x 128 fp32 = 32 KB) in shared memory once and reuses them for every window of its chunk.
 // Each warp owns 4 patches = 16 activation rows per window: it issues all 16 row loads back to back
 // (one 512-byte row = ONE 16-byte load per lane: lanes 0-15 fetch the fp16 "hi" half-row, lanes 16-31
-// the "lo" half-row), multiplies by the staged weights (lanes l and l+16 use the same 8 weights, so
+// the "lo" half-row) and keeps the NEXT window's 16 rows in flight while it multiplies the current ones by the staged weights (lanes l and l+16 use the same 8 weights, so
 // hi*w and lo*w are summed by the final warp-shuffle reduction) and writes 4 scores.
 // All groups walk the windows in the same order, so the ~1.9x re-use of popular rows hits in L2.
 // HBM-bound: 8400 rows x 512 B = 4.3 MB of activation rows per window per IGLOO kernel (2.4 MB distinct).
@@ -30,7 +30,7 @@ constexpr int kGatherThreads = 128;
 constexpr int kGatherSmem = kGatherPB * kPatchLen * kC * 4 + kGatherPB * kPatchLen * 4 + kGatherPB * 4;
 static_assert(kGatherPPG <= kGatherPB, "patch group does not fit the CTA");
 
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 2)
 patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
                     const float* __restrict__ wf,         // [2100][4][128] folded
                     const int32_t* __restrict__ patches,  // [2100][4]
@@ -63,11 +63,21 @@ patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
   const float* wl = s_wf + warp * 16 * kC + l16 * 8;          // this lane's 8 weights of row j: wl[j*128 .. +7]
   const int w_begin = blockIdx.y * windows_per_cta;
   const int w_end = min(n_windows, w_begin + windows_per_cta);
+  const uint8_t* ybase = reinterpret_cast<const uint8_t*>(y);
+  constexpr size_t kWinBytes = static_cast<size_t>(kTok) * kRowHalfs * 2;
+  uint4 nv[16];                                              // rows of the NEXT window, in flight while this one is reduced
+  if (w_begin < w_end) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nv[j] = __ldg(reinterpret_cast<const uint4*>(ybase + w_begin * kWinBytes + rowoff[j]));
+  }
   for (int w = w_begin; w < w_end; ++w) {
-    const uint8_t* yw = reinterpret_cast<const uint8_t*>(y) + static_cast<size_t>(w) * kTok * (kRowHalfs * 2);
     uint4 v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(yw + rowoff[j]));
+    for (int j = 0; j < 16; ++j) v[j] = nv[j];
+    if (w + 1 < w_end) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) nv[j] = __ldg(reinterpret_cast<const uint4*>(ybase + (w + 1) * kWinBytes + rowoff[j]));
+    }
     float acc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
