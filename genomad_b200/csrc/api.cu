@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -51,7 +52,6 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
-  int gather_cta_per_sm = 2;          // patch_gather_kernel keeps its weights in registers (240 regs): 2 CTAs of 128 threads per SM
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_triple = nullptr; float* conv1_bias = nullptr;
@@ -59,7 +59,7 @@ struct gnm_handle {
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
-  float* wf[2] = {nullptr, nullptr}; int32_t* patches[2] = {nullptr, nullptr};
+  float* ent_w[2] = {nullptr, nullptr}; int32_t* ent_pos[2] = {nullptr, nullptr}; int32_t* slot_of[2] = {nullptr, nullptr};
   float* wbias[2] = {nullptr, nullptr}; float* wqk[2] = {nullptr, nullptr};
   float* d0w = nullptr; float* d0b = nullptr; float* bn0_scale = nullptr; float* bn0_shift = nullptr;
   float* d1w = nullptr; float* d1b = nullptr; float* bn1_scale = nullptr; float* bn1_shift = nullptr;
@@ -68,6 +68,7 @@ struct gnm_handle {
   __half* ybuf[2] = {nullptr, nullptr};
   float* q[2] = {nullptr, nullptr};
   float* mpi[2] = {nullptr, nullptr};
+  float* part = nullptr;                             // [max_batch][8880] per-entry partial dot products
   float* logits = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
@@ -216,15 +217,23 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- IGLOO weights
   for (int s = 0; s < 2; ++s) {
     const gnm_igloo_weights& g = w->igloo[s];
-    std::vector<float> wf(static_cast<size_t>(kPatches) * kPatchLen * kC);
-    for (int p = 0; p < kPatches; ++p)
-      for (int k = 0; k < kPatchLen; ++k)
-        for (int c = 0; c < kC; ++c) {
-          const size_t i = (static_cast<size_t>(p) * kPatchLen + k) * kC + c;
-          wf[i] = g.w_mult[i] * g.w_summer[k * kC + c];
-        }
-    if (dev_upload(h, &h->wf[s], wf.data(), wf.size())) return 1;
-    if (dev_upload(h, &h->patches[s], g.patches, static_cast<size_t>(kPatches) * kPatchLen)) return 1;
+    // fold the patch weights, then sort the 8400 (patch, slot) entries by position and deal them to the
+    // 8880 entry slots of patch_stream_kernel (padding slots: position 0, zero weights)
+    std::vector<int> order(static_cast<size_t>(kPatches) * kPatchLen);
+    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g.patches[a] < g.patches[b]; });
+    std::vector<float> ent_w(static_cast<size_t>(kGsSlots) * kC, 0.f);
+    std::vector<int32_t> ent_pos(kGsSlots, 0), slot_of(static_cast<size_t>(kPatches) * kPatchLen, 0);
+    for (size_t slot = 0; slot < order.size(); ++slot) {
+      const int e = order[slot], k = e % kPatchLen;
+      ent_pos[slot] = g.patches[e];
+      slot_of[e] = static_cast<int32_t>(slot);
+      for (int c = 0; c < kC; ++c)
+        ent_w[slot * kC + c] = g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c];
+    }
+    if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
+    if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
+    if (dev_upload(h, &h->slot_of[s], slot_of.data(), slot_of.size())) return 1;
     if (dev_upload(h, &h->wbias[s], g.w_bias, kPatches)) return 1;
     if (dev_upload(h, &h->wqk[s], g.w_qk, static_cast<size_t>(kPatches) * kPooled)) return 1;
     if (dev_upload(h, &h->wv32[s], g.w_v, static_cast<size_t>(kC) * kC)) return 1;
@@ -263,6 +272,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   }
   if (dev_alloc(h, &h->conv_dbg, static_cast<size_t>(h->num_sms) * 8)) return 1;
   GNM_CUDA(cudaMemset(h->conv_dbg, 0, static_cast<size_t>(h->num_sms) * 8 * sizeof(long long)));
+  if (dev_alloc(h, &h->part, mb * kGsSlots)) return 1;
   if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
   if (dev_alloc(h, &h->h0, mb * 256)) return 1;
   if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
@@ -287,7 +297,6 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
-  GNM_CUDA(cudaFuncSetAttribute(patch_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
   GNM_CUDA(cudaDeviceSynchronize());
   return 0;
 }
@@ -382,14 +391,11 @@ static int launch_wv_ref(gnm_handle* h, int s, int in_buf, int n, cudaStream_t s
 }
 
 static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
-  // one resident wave: 148 patch groups x window chunks, gather_cta_per_sm CTAs per SM (33 KB smem, 128 threads each)
-  int chunks = std::max(1, std::min(n, h->gather_cta_per_sm * h->num_sms / kGatherGroups));
-  const int wpc = (n + chunks - 1) / chunks;
-  chunks = (n + wpc - 1) / wpc;
-  dim3 grid(kGatherGroups, chunks);
-  patch_gather_kernel<<<grid, kGatherThreads, kGatherSmem, st>>>(h->ybuf[buf], h->wf[s], h->patches[s], h->wbias[s],
-                                                                h->mpi[s], n, wpc);
-  return check_launch(h, "patch_gather_kernel");
+  patch_stream_kernel<<<kGsGroups, kGsThreads, 0, st>>>(h->ybuf[buf], h->ent_pos[s], h->ent_w[s], h->part, n);
+  if (check_launch(h, "patch_stream_kernel")) return 1;
+  dim3 grid((kPatches + 255) / 256, n);
+  patch_finish_kernel<<<grid, 256, 0, st>>>(h->part, h->slot_of[s], h->wbias[s], h->mpi[s], n);
+  return check_launch(h, "patch_finish_kernel");
 }
 
 static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N,
@@ -570,7 +576,6 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
-  else if (k == "gather_cta_per_sm") h->gather_cta_per_sm = std::max(1, value);
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;

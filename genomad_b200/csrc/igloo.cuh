@@ -13,100 +13,102 @@
 namespace gnm {
 
 // ------------------------------------------------------------------------------------------
-// Patch gather.  Grid = (148 patch groups of <=15 patches) x (window chunks), sized by the host to
-// exactly one resident wave (CTAs of 128 threads, several per SM).  A CTA stages its group's folded weights
-// (<= 16 x 4 x 128 fp32 = 32 KB) in shared memory once and reuses them for every window of its chunk.
-// Each warp owns 4 patches = 16 activation rows per window: it issues all 16 row loads back to back
-// (one 512-byte row = ONE 16-byte load per lane: lanes 0-15 fetch the fp16 "hi" half-row, lanes 16-31
-// the "lo" half-row) and keeps the NEXT window's 16 rows in flight while it multiplies the current ones by the staged weights (lanes l and l+16 use the same 8 weights, so
-// hi*w and lo*w are summed by the final warp-shuffle reduction) and writes 4 scores.
-// All groups walk the windows in the same order, so the ~1.9x re-use of popular rows hits in L2.
-// HBM-bound: 8400 rows x 512 B = 4.3 MB of activation rows per window per IGLOO kernel (2.4 MB distinct).
+// Patch gather, position-ordered streaming form.
+//
+// The 8400 (patch, slot) entries of an IGLOO kernel touch only ~4500 distinct positions, so reading one
+// row per entry moves every popular row ~1.9x through L2 -> SM; the first version (one CTA per 32-patch
+// group, random rows) was bound by exactly that (5 TB/s L2->SM for 2.4 GB of DRAM reads,
+// profiles/r01_small_kernels_ncu.md).  Here the entries are sorted by position on the host and dealt to
+// 444 CTAs x 4 warps x 5 entries (= 3 CTAs per SM, one resident wave, no shared memory): a warp's rows
+// are neighbours in memory, repeats of a row are served by L1, and the whole grid sweeps each window
+// front to back.  Every lane keeps its 5 x 8 folded weights in registers and a 4-window deep ring of
+// row fragments in flight (one 512-byte row = ONE 16-byte load per lane: lanes 0-15 the fp16 "hi"
+// half-row, lanes 16-31 the "lo" half-row; lanes l and l+16 use the same weights, so hi*w and lo*w meet
+// in the warp-shuffle reduction).  Each entry has exactly one writer (part[w][slot]); patch_finish_kernel
+// then adds the four slots of a patch in fixed order k = 0..3 plus the bias, so results are deterministic.
+// HBM-bound: 2.4 MB of distinct activation rows per window per IGLOO kernel (algorithmic 8400 x 512 B = 4.3 MB).
 // ------------------------------------------------------------------------------------------
-constexpr int kGatherGroups = 148;
-constexpr int kGatherPB = 16;                                    // patch slots per CTA (4 warps x 4)
-constexpr int kGatherPPG = (kPatches + kGatherGroups - 1) / kGatherGroups;   // 15 patches per group
-constexpr int kGatherThreads = 128;
-constexpr int kGatherSmem = kGatherPB * kPatchLen * kC * 4 + kGatherPB * kPatchLen * 4 + kGatherPB * 4;
-static_assert(kGatherPPG <= kGatherPB, "patch group does not fit the CTA");
+constexpr int kGsGroups = 444;                                   // CTAs (3 per SM on 148 SMs)
+constexpr int kGsPerWarp = 5;                                    // entries per warp
+constexpr int kGsThreads = 128;
+constexpr int kGsPerCta = 4 * kGsPerWarp;                        // 20
+constexpr int kGsSlots = kGsGroups * kGsPerCta;                  // 8880 >= 8400 (padded with zero-weight entries)
+constexpr int kGsDepth = 4;                                      // windows in flight per warp
+static_assert(kGsSlots >= kPatches * kPatchLen, "not enough entry slots");
 
-__global__ void __launch_bounds__(kGatherThreads, 2)
-patch_gather_kernel(const __half* __restrict__ y,         // [n][5997][256]
-                    const float* __restrict__ wf,         // [2100][4][128] folded
-                    const int32_t* __restrict__ patches,  // [2100][4]
-                    const float* __restrict__ w_bias,     // [2100]
-                    float* __restrict__ mpi,              // [n][2100]
-                    int n_windows, int windows_per_cta) {
-  extern __shared__ __align__(16) uint8_t s_g[];
-  float* s_wf = reinterpret_cast<float*>(s_g);                                    // [16][4][128]
-  int* s_idx = reinterpret_cast<int*>(s_wf + kGatherPB * kPatchLen * kC);          // [16][4]
-  float* s_bias = reinterpret_cast<float*>(s_idx + kGatherPB * kPatchLen);         // [16]
-  const int p0 = blockIdx.x * kGatherPPG;
-  const int np = max(0, min(kGatherPPG, kPatches - p0));
-  for (int i = threadIdx.x; i < kGatherPB * kPatchLen * kC / 4; i += kGatherThreads) {
-    const int pp = i / (kPatchLen * kC / 4);
-    reinterpret_cast<float4*>(s_wf)[i] = pp < np
-        ? reinterpret_cast<const float4*>(wf + static_cast<size_t>(p0) * kPatchLen * kC)[i]
-        : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int i = threadIdx.x; i < kGatherPB * kPatchLen; i += kGatherThreads)
-    s_idx[i] = (i / kPatchLen) < np ? patches[p0 * kPatchLen + i] : 0;
-  for (int i = threadIdx.x; i < kGatherPB; i += kGatherThreads) s_bias[i] = i < np ? w_bias[p0 + i] : 0.f;
-  __syncthreads();
-
+__global__ void __launch_bounds__(kGsThreads, 3)
+patch_stream_kernel(const __half* __restrict__ y,          // [n][5997][256]
+                    const int32_t* __restrict__ ent_pos,   // [8880] position of each slot (0 for padding)
+                    const float* __restrict__ ent_w,       // [8880][128] folded weights of each slot (0 for padding)
+                    float* __restrict__ part,              // [n][8880]
+                    int n_windows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, l16 = lane & 15;               // half 0: "hi" plane, 1: "lo" plane
-  int rowoff[16];                                            // byte offset of this lane's 16 B inside each of the 16 rows
+  const int half = lane >> 4, l16 = lane & 15;
+  const int e0 = blockIdx.x * kGsPerCta + warp * kGsPerWarp;
+  int rowoff[kGsPerWarp];
+  float wt[kGsPerWarp][8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    rowoff[j] = s_idx[warp * 16 + j] * (kRowHalfs * 2) + half * (kC * 2) + l16 * 16;
-  const float* wl = s_wf + warp * 16 * kC + l16 * 8;          // this lane's 8 weights of row j: wl[j*128 .. +7]
-  const int w_begin = blockIdx.y * windows_per_cta;
-  const int w_end = min(n_windows, w_begin + windows_per_cta);
+  for (int i = 0; i < kGsPerWarp; ++i) {
+    rowoff[i] = ent_pos[e0 + i] * (kRowHalfs * 2) + half * (kC * 2) + l16 * 16;
+    const float4 a = *reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(e0 + i) * kC + l16 * 8);
+    const float4 b = *reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(e0 + i) * kC + l16 * 8 + 4);
+    wt[i][0] = a.x; wt[i][1] = a.y; wt[i][2] = a.z; wt[i][3] = a.w;
+    wt[i][4] = b.x; wt[i][5] = b.y; wt[i][6] = b.z; wt[i][7] = b.w;
+  }
   const uint8_t* ybase = reinterpret_cast<const uint8_t*>(y);
   constexpr size_t kWinBytes = static_cast<size_t>(kTok) * kRowHalfs * 2;
-  uint4 nv[16];                                              // rows of the NEXT window, in flight while this one is reduced
-  if (w_begin < w_end) {
+  uint4 ring[kGsDepth][kGsPerWarp];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) nv[j] = __ldg(reinterpret_cast<const uint4*>(ybase + w_begin * kWinBytes + rowoff[j]));
-  }
-  for (int w = w_begin; w < w_end; ++w) {
-    uint4 v[16];
+  for (int d = 0; d < kGsDepth; ++d)
+    if (d < n_windows) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = nv[j];
-    if (w + 1 < w_end) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) nv[j] = __ldg(reinterpret_cast<const uint4*>(ybase + (w + 1) * kWinBytes + rowoff[j]));
+      for (int i = 0; i < kGsPerWarp; ++i)
+        ring[d][i] = __ldg(reinterpret_cast<const uint4*>(ybase + d * kWinBytes + rowoff[i]));
     }
-    float acc[4];
+  for (int w0 = 0; w0 < n_windows; w0 += kGsDepth) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = 0.f;
+    for (int d = 0; d < kGsDepth; ++d) {
+      const int w = w0 + d;
+      if (w < n_windows) {
+        float acc[kGsPerWarp];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = i * 4 + k;
-        const float4 w0 = *reinterpret_cast<const float4*>(wl + j * kC);
-        const float4 w1 = *reinterpret_cast<const float4*>(wl + j * kC + 4);
-        const __half2* h = reinterpret_cast<const __half2*>(&v[j]);
-        a = fmaf(__low2float(h[0]), w0.x, a); a = fmaf(__high2float(h[0]), w0.y, a);
-        a = fmaf(__low2float(h[1]), w0.z, a); a = fmaf(__high2float(h[1]), w0.w, a);
-        a = fmaf(__low2float(h[2]), w1.x, a); a = fmaf(__high2float(h[2]), w1.y, a);
-        a = fmaf(__low2float(h[3]), w1.z, a); a = fmaf(__high2float(h[3]), w1.w, a);
-      }
-      acc[i] = a;
-    }
+        for (int i = 0; i < kGsPerWarp; ++i) {
+          const __half2* h = reinterpret_cast<const __half2*>(&ring[d][i]);
+          float a = __low2float(h[0]) * wt[i][0];
+          a = fmaf(__high2float(h[0]), wt[i][1], a);
+          a = fmaf(__low2float(h[1]), wt[i][2], a); a = fmaf(__high2float(h[1]), wt[i][3], a);
+          a = fmaf(__low2float(h[2]), wt[i][4], a); a = fmaf(__high2float(h[2]), wt[i][5], a);
+          a = fmaf(__low2float(h[3]), wt[i][6], a); a = fmaf(__high2float(h[3]), wt[i][7], a);
+          acc[i] = a;
+        }
+        if (w + kGsDepth < n_windows) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
+          for (int i = 0; i < kGsPerWarp; ++i)
+            ring[d][i] = __ldg(reinterpret_cast<const uint4*>(ybase + (w + kGsDepth) * kWinBytes + rowoff[i]));
+        }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-    if (lane < 4) {
-      const int pl = warp * 4 + lane;
-      if (pl < np) {
-        const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        mpi[static_cast<size_t>(w) * kPatches + p0 + pl] = r + s_bias[pl];
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int i = 0; i < kGsPerWarp; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+        if (lane < kGsPerWarp) {
+          const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
+          part[static_cast<size_t>(w) * kGsSlots + e0 + lane] = r;
+        }
       }
     }
   }
+}
+
+// mpi[w][p] = ((part[s0] + part[s1]) + part[s2]) + part[s3] + bias[p],  s_k = slot_of[4p + k]
+__global__ void __launch_bounds__(256)
+patch_finish_kernel(const float* __restrict__ part, const int32_t* __restrict__ slot_of, const float* __restrict__ w_bias,
+                    float* __restrict__ mpi, int n_windows) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = blockIdx.y;
+  if (p >= kPatches) return;
+  const float* pw = part + static_cast<size_t>(w) * kGsSlots;
+  const int4 s4 = *reinterpret_cast<const int4*>(slot_of + p * 4);
+  mpi[static_cast<size_t>(w) * kPatches + p] = (((pw[s4.x] + pw[s4.y]) + pw[s4.z]) + pw[s4.w]) + w_bias[p];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -55,7 +55,9 @@ def init_process_group_if_needed(backend: Optional[str] = None) -> DistInfo:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(info.local_rank)
-            dist.init_process_group(backend=backend)
+                dist.init_process_group(backend=backend, device_id=torch.device("cuda", info.local_rank))
+            else:
+                dist.init_process_group(backend=backend)
     return info
 
 

@@ -27,18 +27,6 @@ for exp in [int(x) for x in (sys.argv[1:] or ["0", "2"])]:
     clf.set_option("profile_stages", 0)
     print(f"experiment={exp}: " + "  ".join(f"{k}={sum(v)/len(v):.3f}" for k, v in acc.items()), flush=True)
 
-for g in (2, 3, 4, 5, 6):
-    clf.set_option("conv_experiment", 0)
-    clf.set_option("gather_cta_per_sm", g)
-    clf.predict_ascii(a, out)
-    clf.set_option("profile_stages", 1)
-    for _ in range(3):
-        clf.predict_ascii(a, out)
-    torch.cuda.synchronize()
-    t = [ms for name, ms in clf.stage_times() if name.startswith("gather")]
-    clf.set_option("profile_stages", 0)
-    print(f"gather_cta_per_sm={g}: gather mean {sum(t)/len(t):.3f} ms", flush=True)
-
 # cycle breakdown of the MMA issuer / epilogue (experiment bit 4)
 clf.set_option("conv_experiment", 4)
 clf.predict_ascii(a, out); torch.cuda.synchronize()
