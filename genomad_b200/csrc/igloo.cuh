@@ -26,6 +26,10 @@ namespace gnm {
 // half-row, lanes 16-31 the "lo" half-row; lanes l and l+16 use the same weights, so hi*w and lo*w meet
 // in the warp-shuffle reduction).  Each entry has exactly one writer (part[w][slot]); patch_finish_kernel
 // then adds the four slots of a patch in fixed order k = 0..3 plus the bias, so results are deterministic.
+// Measured (profiles/r01_small_kernels_ncu.md): 0.74 ms per 1024 windows = 3.2 TB/s of DRAM reads, 40 % of peak.
+// A variant that staged the rows with 512-byte cp.async.bulk copies (6 windows deep, 184 KB in flight per SM)
+// was slower (0.88 ms), i.e. the limit is not outstanding-load capacity but DRAM efficiency on 512-byte pieces
+// requested by many CTAs at once; reading each CTA's position range as one contiguous block is the next step.
 // HBM-bound: 2.4 MB of distinct activation rows per window per IGLOO kernel (algorithmic 8400 x 512 B = 4.3 MB).
 // ------------------------------------------------------------------------------------------
 constexpr int kGsGroups = 444;                                   // CTAs (3 per SM on 148 SMs)
