@@ -17,7 +17,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libgnm.so"
-SOURCES = [CSRC / "api.cu"]
+SOURCES = [CSRC / "api.cu", CSRC / "fasta.cpp"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "gnm.h"]
 
 NVCC_FLAGS = [
@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-    "-lcudart",
+    "-lcudart", "-Xcompiler", "-pthread",
 ]
 
 

@@ -56,13 +56,17 @@ def _write_tsv(path: Path, names, preds) -> None:
             fout.write(f"{name}\t{float(s[0]):.4f}\t{float(s[1]):.4f}\t{float(s[2]):.4f}\n")
 
 
-def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_window, names_key, ids_key, what, is_main):
+def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_window, names_key, ids_key, what, is_main,
+                  parsed=None):
     if enc_dir.is_dir() and is_main:
         shutil.rmtree(enc_dir)
     console.log(f"Creating the {enc_dir} directory.")
     if is_main:
         enc_dir.mkdir()
-    enc = sequence.encode_fasta(fasta_path, single_window)
+    if parsed is None:
+        parsed = sequence.ParsedFasta(fasta_path, single_window)
+    enc = parsed.encode()
+    parsed.close()
     if is_main:
         np.savez_compressed(id_path, **{names_key: enc.names, ids_key: enc.contig_ids})
         np.save(enc_dir / f"{len(enc.contig_ids)}.windows.npy", enc.windows)
@@ -109,7 +113,8 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                          "This will classify the input sequences into chromosome, plasmid, or virus based on the "
                          "nucleotide sequence.", outputs.nn_classification_dir, files, descr)
 
-    if not sequence.check_fasta(input_path):
+    parsed_input = sequence.ParsedFasta(input_path, single_window)      # one native pass: check + windows
+    if not parsed_input.check():
         console.error(f"{input_path} is either empty or contains multiple entries with the same identifier. "
                       "Please check your input FASTA file and execute genomad nn-classification again.")
         sys.exit(1)
@@ -155,7 +160,8 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             if not (skip and npz_path.exists()):
                 enc = _load_encoded(enc_dir, id_path, names_key, ids_key)
         else:
-            enc = _encode_stage(console, fasta, enc_dir, id_path, single_window, names_key, ids_key, what, is_main)
+            enc = _encode_stage(console, fasta, enc_dir, id_path, single_window, names_key, ids_key, what, is_main,
+                                parsed=parsed_input if what == "sequence" else None)
         # ---- classify
         if skip and npz_path.exists():
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")

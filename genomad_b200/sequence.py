@@ -15,9 +15,12 @@ vectors made with the real reference code (tests/golden/encoder_golden.json):
     RAW text (lower-case ``n`` does not count) -- nn_classification.py:70-71;
   * windows are upper-cased and right-padded with ``N`` to 6000 bytes (nn_classification.py:72).
 
-Unlike the reference (a Python generator of ``Sequence`` objects feeding a per-window numba call), this
-works on bytes with C-speed primitives and emits one dense uint8 matrix [n_windows, 6000] that is
-shipped to the GPU as is -- tokenisation happens on the device (csrc/encode.cuh).
+Unlike the reference (a Python generator of ``Sequence`` objects feeding a per-window numba call), the
+production path (``ParsedFasta`` / ``encode_fasta``) is native code in libgnm.so (csrc/fasta.cpp): one
+multi-threaded pass over the file text that writes one dense uint8 matrix [n_windows, 6000], which is shipped
+to the GPU as is -- tokenisation happens on the device (csrc/encode.cuh).  ``iter_fasta`` / ``window_spans`` /
+``encode_fasta_py`` are the readable pure-Python statement of the same rules; the tests hold the native code
+to them and both to golden vectors made with the real reference.
 """
 from __future__ import annotations
 
@@ -130,11 +133,8 @@ class EncodedFasta:
     windows: np.ndarray      # [n_windows, 6000] uint8 -- upper-cased, N-padded ASCII
 
 
-def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = None) -> EncodedFasta:
-    """
-    FASTA -> dense window matrix, the device-resident analogue of generate_data()
-    (reference nn_classification.py:54-82; the TFRecord round trip is gone).
-    """
+def encode_fasta_py(path, single_window: bool = False, out: Optional[np.ndarray] = None) -> EncodedFasta:
+    """Pure-Python statement of encode_fasta (specification / cross-check for the native reader)."""
     names: List[str] = []
     ids: List[int] = []
     pieces: List[bytes] = []
@@ -161,3 +161,72 @@ def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = 
     offsets = np.zeros(len(names) + 1, dtype=np.int32)
     np.cumsum(counts, out=offsets[1:])
     return EncodedFasta(np.array(names), cid_arr, offsets, win)
+
+
+class ParsedFasta:
+    """
+    One native pass over a FASTA file (libgnm.so, csrc/fasta.cpp): answers check_fasta() and produces the window
+    matrix without re-reading the file.  The analogue of check_fasta + generate_data()
+    (reference sequence.py:124-131, nn_classification.py:54-82; the TFRecord round trip is gone).
+    """
+
+    def __init__(self, path, single_window: bool = False, threads: Optional[int] = None):
+        import ctypes as C
+        import os
+        from . import engine
+        self._lib = engine.load_library()
+        self._text = read_bytes(path)                       # kept alive: the parser points into it
+        self._threads = int(threads or min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8))
+        self._h = C.c_void_p()
+        buf = self._text
+        rc = self._lib.gnm_fasta_parse(C.cast(C.c_char_p(buf), C.c_void_p), len(buf), int(bool(single_window)),
+                                       self._threads, C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
+        nrec, dup, nc, nw, hb = C.c_int64(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._lib.gnm_fasta_info(self._h, C.byref(nrec), C.byref(dup), C.byref(nc), C.byref(nw), C.byref(hb))
+        self.n_records, self.has_duplicate_ids = nrec.value, bool(dup.value)
+        self.n_contigs, self.n_windows, self._header_bytes = nc.value, nw.value, hb.value
+
+    def check(self) -> bool:
+        """reference check_fasta(): at least one record and no repeated identifier."""
+        return self.n_records > 0 and not self.has_duplicate_ids
+
+    def encode(self, out: Optional[np.ndarray] = None) -> EncodedFasta:
+        import ctypes as C
+        n, nc = self.n_windows, self.n_contigs
+        if out is not None:
+            assert out.dtype == np.uint8 and out.shape[0] >= n and out.shape[1] == WINDOW and out.flags.c_contiguous
+            win = out[:n]
+        else:
+            win = np.empty((n, WINDOW), dtype=np.uint8)
+        offsets = np.zeros(nc + 1, dtype=np.int32)
+        headers = C.create_string_buffer(max(1, self._header_bytes))
+        rc = self._lib.gnm_fasta_export(self._h, win.ctypes.data if n else None, offsets.ctypes.data, headers, self._threads)
+        if rc != 0:
+            raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
+        lines = headers.raw[: self._header_bytes].decode("utf-8", errors="replace").split("\n")[:nc]
+        names = np.array([accession(h) for h in lines]) if nc else np.array([], dtype="<U1")
+        ids = np.repeat(np.arange(nc, dtype=np.int64), np.diff(offsets))
+        return EncodedFasta(names, ids, offsets, win)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gnm_fasta_free(self._h)
+            self._h = None
+        self._text = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = None) -> EncodedFasta:
+    """FASTA -> dense window matrix (native)."""
+    p = ParsedFasta(path, single_window)
+    try:
+        return p.encode(out)
+    finally:
+        p.close()

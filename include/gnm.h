@@ -124,6 +124,26 @@ int gnm_segment_sum(gnm_handle* h, const float* d_probs, const int32_t* d_offset
  */
 int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_probs);
 
+/* ---- host-side FASTA front end (no GPU involved) ------------------------------------------ */
+
+/*
+ * FASTA text (already decompressed, `len` bytes, must stay alive until gnm_fasta_free) -> windows.
+ * Replaces the Python loop read_fasta(strip_n=True) -> seq_windows(6000, 2500) -> N rule -> upper-case + pad
+ * (sequence.py:96-167, nn_classification.py:65-72); multi-threaded, single pass over the text.
+ *   gnm_fasta_info   : n_records_nonempty / has_duplicate_ids are what check_fasta() tests (sequence.py:124-131);
+ *                      n_contigs = records kept after stripping n/N; header_bytes = size of the headers export.
+ *   gnm_fasta_export : windows uint8 [n_windows][6000] (may be pinned memory), offsets int32 [n_contigs + 1],
+ *                      headers = the kept records' header lines joined with '\n' (header_bytes bytes); any pointer
+ *                      may be NULL to skip that output.
+ */
+typedef struct gnm_fasta gnm_fasta;
+const char* gnm_fasta_last_error(void);
+int gnm_fasta_parse(const uint8_t* text, size_t len, int single_window, int threads, gnm_fasta** out);
+int gnm_fasta_info(const gnm_fasta* f, int64_t* n_records_nonempty, int* has_duplicate_ids, int64_t* n_contigs,
+                   int64_t* n_windows, int64_t* header_bytes);
+int gnm_fasta_export(const gnm_fasta* f, uint8_t* windows, int32_t* offsets, char* headers, int threads);
+void gnm_fasta_free(gnm_fasta* f);
+
 /* ---- introspection / test hooks (not needed by a drop-in caller) ------------------------- */
 
 /* Options: "conv_impl" 0 = tcgen05 tensor-core path (default), 1 = fp32 CUDA-core validation

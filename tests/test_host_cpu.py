@@ -254,3 +254,67 @@ def test_cli_options_match_reference():
     for opt in ("--restart", "--threads", "-t", "--verbose", "--quiet", "-v", "-q", "--cleanup", "--single-window",
                 "--batch-size", "INPUT", "OUTPUT"):
         assert opt in r.output, opt
+
+
+# ------------------------------------------------------------------------------------------ native FASTA reader
+def test_native_fasta_matches_reference_golden(enc, tmp_path):
+    """csrc/fasta.cpp against the records the REAL reference reader produced (incl. CRLF, junk before '>', empty records)."""
+    for name, case in enc["fasta"].items():
+        p = tmp_path / f"{name}.fna"
+        p.write_text(case["text"], newline="")
+        pf = sequence.ParsedFasta(p)
+        e = pf.encode()
+        want = [(r[1], r[2]) for r in case["records"]]
+        assert list(e.names) == [w[0] for w in want], name
+        assert pf.check() == case["check_fasta"], name
+        got_first = [bytes(e.windows[e.offsets[i]]).rstrip(b"N")[:len(w[1])] for i, w in enumerate(want)]
+        for g, w in zip(got_first, want):
+            stripped = w[1].upper()[:6000].rstrip("N").encode()
+            assert g[:len(stripped)] == stripped, name
+
+
+def test_native_fasta_equals_python_statement_and_oracle(enc, tmp_path):
+    rng = np.random.default_rng(8)
+    recs = []
+    for i, ln in enumerate([10000, 400, 2499, 2500, 14500, 6000, 30000, 8499, 1, 12000]):
+        s = np.frombuffer(b"ACGTNacgtnRY-", np.uint8)[rng.choice(13, ln, p=[.2, .2, .2, .2, .04, .03, .03, .03, .03, .01, .01, .01, .01])]
+        width = int(rng.integers(20, 90))
+        recs.append(f">c{i}\tdesc {i}\n" + "\n".join(s.tobytes().decode()[k:k + width] for k in range(0, ln, width)))
+    for case in enc["nrule"]:
+        recs.append(f">{case['name']}\n{case['raw']}")
+    recs.append(">only_n\nNNNNnnnn")
+    recs.append(">empty")
+    text = "leading junk\n" + "\n".join(recs) + "\n"
+    for eol in ("\n", "\r\n", "\r"):
+        p = tmp_path / "mix.fna"
+        p.write_text(text.replace("\n", eol), newline="")
+        for single in (False, True):
+            a = sequence.encode_fasta(p, single_window=single)            # native
+            b = sequence.encode_fasta_py(p, single_window=single)         # python statement
+            names, ids, ascii_arr, _ = T.encode_fasta(p, single_window=single)   # oracle (reference transcription)
+            for x in (b,):
+                assert list(a.names) == list(x.names) and np.array_equal(a.offsets, x.offsets)
+                assert np.array_equal(a.contig_ids, x.contig_ids) and np.array_equal(a.windows, x.windows)
+            assert list(a.names) == list(names) and np.array_equal(a.contig_ids, ids) and np.array_equal(a.windows, ascii_arr)
+    for case in enc["nrule"]:
+        q = tmp_path / "n.fna"
+        q.write_text(f">x\n{case['raw']}\n")
+        assert sequence.ParsedFasta(q).n_windows == len(case["kept"]), case["name"]
+
+
+def test_native_fasta_check_and_gzip(tmp_path):
+    d = tmp_path / "dup.fna"
+    d.write_text(">a 1\nACGT\n>a 2\nGGGG\n")
+    assert not sequence.ParsedFasta(d).check() and not sequence.check_fasta(d)
+    e = tmp_path / "empty.fna"
+    e.write_text("no header here\n")
+    pf = sequence.ParsedFasta(e)
+    assert not pf.check() and pf.n_windows == 0 and pf.encode().windows.shape == (0, 6000)
+    g = tmp_path / "z.fna.gz"
+    with gzip.open(g, "wt") as fh:
+        fh.write(">k x\nnnACGTacgtNN\n")
+    enc_ = sequence.encode_fasta(g)
+    assert list(enc_.names) == ["k"] and bytes(enc_.windows[0][:8]) == b"ACGTACGT" and enc_.windows[0][8] == ord("N")
+    out = np.zeros((4, 6000), np.uint8)
+    enc2 = sequence.ParsedFasta(g).encode(out)
+    assert enc2.windows.base is out or np.shares_memory(enc2.windows, out)
