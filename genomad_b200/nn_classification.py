@@ -30,6 +30,23 @@ def _make_classifier(batch_size: int, device: int):
     return Classifier(None, device=device, max_batch=max(1, int(batch_size)))
 
 
+def _pinned_windows(n: int):
+    """uint8 [n, 6000] in page-locked host memory when a GPU is present (H2D copies then overlap compute)."""
+    try:
+        import torch
+        if n > 0 and torch.cuda.is_available():
+            t = torch.empty((n, sequence.WINDOW), dtype=torch.uint8).pin_memory()
+            arr = t.numpy()
+            _PINNED_KEEPALIVE.append(t)
+            return arr
+    except Exception:
+        pass
+    return None
+
+
+_PINNED_KEEPALIVE: list = []
+
+
 def _classify_windows(clf, windows: np.ndarray, offsets: np.ndarray, info: gdist.DistInfo,
                       contig_reduce: str = "gather") -> np.ndarray:
     """windows uint8 [W,6000] + contig offsets -> float32 [n_contigs,3] per-contig mean (identical on all ranks)."""
@@ -65,7 +82,7 @@ def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_wind
         enc_dir.mkdir()
     if parsed is None:
         parsed = sequence.ParsedFasta(fasta_path, single_window)
-    enc = parsed.encode()
+    enc = parsed.encode(_pinned_windows(parsed.n_windows))      # written straight into page-locked memory
     parsed.close()
     if is_main:
         np.savez_compressed(id_path, **{names_key: enc.names, ids_key: enc.contig_ids})
@@ -187,4 +204,5 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             _write_tsv(tsv_path, names, preds)
         console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
 
+    _PINNED_KEEPALIVE.clear()
     console.log("geNomad nn-classification finished!")
