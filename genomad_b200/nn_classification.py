@@ -74,7 +74,7 @@ def _write_tsv(path: Path, names, preds) -> None:
 
 
 def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_window, names_key, ids_key, what, is_main,
-                  parsed=None):
+                  parsed=None, keep_windows=True):
     if enc_dir.is_dir() and is_main:
         shutil.rmtree(enc_dir)
     console.log(f"Creating the {enc_dir} directory.")
@@ -86,7 +86,8 @@ def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_wind
     parsed.close()
     if is_main:
         np.savez_compressed(id_path, **{names_key: enc.names, ids_key: enc.contig_ids})
-        np.save(enc_dir / f"{len(enc.contig_ids)}.windows.npy", enc.windows)
+        if keep_windows:                  # with --cleanup the directory is deleted right after classification
+            np.save(enc_dir / f"{len(enc.contig_ids)}.windows.npy", enc.windows)
     console.log(f"Encoded {what} data written to {enc_dir.name}.")
     return enc
 
@@ -178,7 +179,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                 enc = _load_encoded(enc_dir, id_path, names_key, ids_key)
         else:
             enc = _encode_stage(console, fasta, enc_dir, id_path, single_window, names_key, ids_key, what, is_main,
-                                parsed=parsed_input if what == "sequence" else None)
+                                parsed=parsed_input if what == "sequence" else None, keep_windows=not cleanup)
         # ---- classify
         if skip and npz_path.exists():
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")

@@ -66,7 +66,20 @@ class HybridConsole:
         self._write_file(line)
 
 
+_MD5_CACHE: dict = {}
+
+
 def get_md5(path, size: int = 1 << 20) -> str:
+    """md5 of a file; memoised on (path, size, mtime) -- the reference re-hashes the input up to three times per run."""
+    st = os.stat(path)
+    key = (str(Path(path).resolve()), st.st_size, st.st_mtime_ns)
+    if key in _MD5_CACHE:
+        return _MD5_CACHE[key]
+    _MD5_CACHE[key] = digest = _md5_uncached(path, size)
+    return digest
+
+
+def _md5_uncached(path, size: int = 1 << 20) -> str:
     m = hashlib.md5()
     with open(path, "rb") as fin:
         while True:
