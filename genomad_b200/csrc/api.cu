@@ -55,7 +55,8 @@ struct gnm_handle {
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_triple = nullptr; float* conv1_bias = nullptr;
-  __half* wpack[4] = {nullptr, nullptr, nullptr, nullptr};   // conv2, conv3, w_v#0, w_v#1 -- TMA stage order
+  uint8_t* wpack[4] = {nullptr, nullptr, nullptr, nullptr};  // conv2, conv3, w_v#0, w_v#1 -- 16 KB TMA stages in consumption order
+  float conv_out_scale[2] = {1.f, 1.f};             // 2^-S per conv layer (see conv_t.cuh)
   float* conv_bias[2] = {nullptr, nullptr};
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
@@ -65,7 +66,8 @@ struct gnm_handle {
   float* d1w = nullptr; float* d1b = nullptr; float* bn1_scale = nullptr; float* bn1_shift = nullptr;
   float* d2w = nullptr; float* d2b = nullptr;
   // workspace
-  __half* ybuf[2] = {nullptr, nullptr};
+  uint8_t* ybuf[2] = {nullptr, nullptr};            // activation rows, 768 B per position
+  int ybuf_fp8lo[2] = {0, 0};                        // 1 = the buffer was written by conv2 (hi16 + lo8 + hi8 only)
   float* q[2] = {nullptr, nullptr};
   float* mpi[2] = {nullptr, nullptr};
   float* part = nullptr;                             // [max_batch][8880] per-entry partial dot products
@@ -112,39 +114,51 @@ static int get_encode_fn(PFN_encodeTiled* fn) {
   return 0;
 }
 
-// activations [n][5997][256] fp16; box = 64 channels x 136 rows x 1 window, 128B swizzle, OOB rows -> 0
-static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, __half* base, int n_windows) {
-  cuuint64_t dims[3] = {kRowHalfs, kTok, static_cast<cuuint64_t>(n_windows)};
-  cuuint64_t strides[2] = {kRowHalfs * sizeof(__half), static_cast<cuuint64_t>(kTok) * kRowHalfs * sizeof(__half)};
-  cuuint32_t box[3] = {64, kSlabRows, 1};
+// activations [n][5997][768 B] viewed as bytes; box = 128 bytes (one plane slice) x 136 rows x 1 window, 128B swizzle,
+// rows outside [0, 5997) read as 0 (= causal padding)
+static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows) {
+  cuuint64_t dims[3] = {kRowBytes, kTok, static_cast<cuuint64_t>(n_windows)};
+  cuuint64_t strides[2] = {kRowBytes, static_cast<cuuint64_t>(kTok) * kRowBytes};
+  cuuint32_t box[3] = {128, kSlabRows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activations) failed: " + std::to_string(int(r)));
   return 0;
 }
-// packed weights [stages*128 rows][64] fp16; box = 64 x 128
-static int make_w_map(PFN_encodeTiled enc, CUtensorMap* tm, __half* base, int n_stages) {
-  cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(n_stages) * 128};
-  cuuint64_t strides[1] = {64 * sizeof(__half)};
-  cuuint32_t box[2] = {64, 128};
+// packed weights [stages*128 rows][128 B]; box = 128 B x 128 rows
+static int make_w_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_stages) {
+  cuuint64_t dims[2] = {128, static_cast<cuuint64_t>(n_stages) * 128};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {128, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
   return 0;
 }
 
-// One 16 KB TMA stage: B[n][kk] = part(W[k = kh*64 + kk][n]), part = hi or lo of the fp16 split.
-static void pack_stage(std::vector<__half>& dst, const float* Wkn /* [128 k][128 n] */, int w_lo, int kh) {
+// One 16 KB fp16 TMA stage: B[n][kk] = fp16(part(W[k = kh*64 + kk][n]) * scale), part = hi or lo of the fp16 split.
+static void pack_stage_f16(std::vector<uint8_t>& dst, const float* Wkn /* [128 k][128 n] */, int w_lo, int kh, float scale) {
   for (int n = 0; n < kC; ++n)
     for (int kk = 0; kk < 64; ++kk) {
       const float x = Wkn[static_cast<size_t>(kh * 64 + kk) * kC + n];
       const __half hi = __float2half_rn(x);
-      const __half lo = __float2half_rn(x - __half2float(hi));
-      dst.push_back(w_lo ? lo : hi);
+      const float v = (w_lo ? x - __half2float(hi) : __half2float(hi)) * scale;
+      const uint16_t bits = __half_as_ushort(__float2half_rn(v));
+      dst.push_back(static_cast<uint8_t>(bits & 0xff));
+      dst.push_back(static_cast<uint8_t>(bits >> 8));
+    }
+}
+// One 16 KB e4m3 TMA stage: B[n][k] = e4m3(part(W[k][n]) * scale), all 128 input channels in one 128-byte row.
+static void pack_stage_f8(std::vector<uint8_t>& dst, const float* Wkn, int w_lo, float scale) {
+  for (int n = 0; n < kC; ++n)
+    for (int k = 0; k < kC; ++k) {
+      const float x = Wkn[static_cast<size_t>(k) * kC + n];
+      const float hi = __half2float(__float2half_rn(x));
+      dst.push_back(static_cast<uint8_t>(__nv_cvt_float_to_fp8((w_lo ? x - hi : hi) * scale, __NV_SATFINITE, __NV_E4M3)));
     }
 }
 
@@ -197,18 +211,30 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   {
     const float* convw[2] = {w->conv2_kernel, w->conv3_kernel};
     for (int L = 0; L < 2; ++L) {
-      std::vector<__half> pk;                              // conv: (K-half, tap, weight hi/lo)
-      pk.reserve(static_cast<size_t>(kConvStages) * 128 * 64);
+      // common scale 2^S of the three passes (conv_t.cuh): main weights fp16(Whi * 2^d), d = 16 for |W| < 0.78
+      float wmax = 0.f;
+      for (size_t i = 0; i < static_cast<size_t>(kTaps) * kC * kC; ++i) wmax = std::max(wmax, std::fabs(convw[L][i]));
+      if (!(wmax > 0.f) || !std::isfinite(wmax)) return fail("gnm_create: conv kernel is all-zero or not finite");
+      const int shift = std::max(0, static_cast<int>(std::ceil(std::log2(wmax / 0.78f))));
+      const int d = 16 - shift, S = 5 + d;
+      if (d < 1) return fail("gnm_create: conv weights too large for the fp16 operand format");
+      h->conv_out_scale[L] = std::ldexp(1.f, -S);
+      std::vector<uint8_t> pk;                              // (region, tap): hi16.k0 x6, hi16.k1 x6, lo8 x6, hi8 x6
+      pk.reserve(static_cast<size_t>(kConvStages) * kBStage);
       for (int kh = 0; kh < 2; ++kh)
         for (int tap = 0; tap < kTaps; ++tap)
-          for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, w_lo, kh);
+          pack_stage_f16(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 0, kh, std::ldexp(1.f, d));
+      for (int tap = 0; tap < kTaps; ++tap)                 // x lo8 = e4m3(Alo * 2^12):  e4m3(Whi * 2^(S-12))
+        pack_stage_f8(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 0, std::ldexp(1.f, S - 12));
+      for (int tap = 0; tap < kTaps; ++tap)                 // x hi8 = e4m3(Ahi * 2^7):   e4m3(Wlo * 2^(S-7))
+        pack_stage_f8(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 1, std::ldexp(1.f, S - 7));
       if (dev_upload(h, &h->wpack[L], pk.data(), pk.size())) return 1;
       if (dev_upload(h, &h->conv_w32[L], convw[L], static_cast<size_t>(kTaps) * kC * kC)) return 1;
     }
-    for (int s = 0; s < 2; ++s) {                          // w_v: (K-half, weight hi/lo)
-      std::vector<__half> pk;
+    for (int s = 0; s < 2; ++s) {                          // w_v: (K-half, weight hi/lo), unscaled fp16
+      std::vector<uint8_t> pk;
       for (int kh = 0; kh < 2; ++kh)
-        for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage(pk, w->igloo[s].w_v, w_lo, kh);
+        for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage_f16(pk, w->igloo[s].w_v, w_lo, kh, 1.f);
       if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
     }
     if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
@@ -229,7 +255,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
       ent_pos[slot] = g.patches[e];
       slot_of[e] = static_cast<int32_t>(slot);
       for (int c = 0; c < kC; ++c)
-        ent_w[slot * kC + c] = g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c];
+        ent_w[slot * kC + c] = (g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c]) * (1.f / kActScale);
     }
     if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
     if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
@@ -262,7 +288,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- workspace
   const size_t mb = static_cast<size_t>(max_batch);
   for (int i = 0; i < 2; ++i) {
-    if (dev_alloc(h, &h->ybuf[i], mb * kTok * kRowHalfs)) return 1;
+    if (dev_alloc(h, &h->ybuf[i], mb * kTok * kRowBytes)) return 1;
     if (dev_alloc(h, &h->q[i], mb * kPooled * kC)) return 1;
     if (dev_alloc(h, &h->mpi[i], mb * kPatches)) return 1;
     if (dev_alloc(h, &h->in_stage[i], mb * kWindow)) return 1;
@@ -336,7 +362,7 @@ static void timer_mark(gnm_handle* h, const char* name, cudaStream_t st) {
   t.names.push_back(name);
 }
 
-// layer 0: conv2 (y[in] -> y[1-in]); layer 1: conv3
+// layer 0: conv2 (y[in] -> y[1-in], planes hi16 + lo8 + hi8 for conv3); layer 1: conv3 (planes hi16 + lo16)
 static int launch_conv(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t st) {
   ConvTcParams p;
   p.n_tiles = n * kUnitsPerWin;                  // 256-position units
@@ -346,6 +372,9 @@ static int launch_conv(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t
   p.bias = h->conv_bias[layer];
   p.y_out = h->ybuf[1 - in_buf];
   p.q_out = nullptr;
+  p.out_scale = h->conv_out_scale[layer];
+  p.out_fp8 = layer == 0 ? 1 : 0;
+  h->ybuf_fp8lo[1 - in_buf] = p.out_fp8;
   const int grid = std::min(h->num_sms, p.n_tiles);
   conv_t_kernel<false><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[in_buf], h->tm_w[layer], p);
   return check_launch(h, "conv_t_kernel<false>");
@@ -357,6 +386,8 @@ static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   p.experiment = 0;
   p.dbg = nullptr;
   p.bias = nullptr; p.y_out = nullptr; p.q_out = h->q[s];
+  p.out_scale = 1.f / kActScale;
+  p.out_fp8 = 0;
   p.n_tiles = n * kUnitsPerWin;
   const int grid = std::min(h->num_sms, p.n_tiles);
   conv_t_kernel<true><<<grid, kConvThreads, kConvTSmem, st>>>(h->tm_act[buf], h->tm_w[2 + s], p);
@@ -416,6 +447,7 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
                         cudaStream_t st) {
   h->last_n = n;
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
+  h->ybuf_fp8lo[0] = h->ybuf_fp8lo[1] = 0;
   timer_mark(h, "embed_conv1", st);
   if (d_ascii)
     embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
@@ -624,7 +656,8 @@ extern "C" int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d
   size_t count = 0;
   if (k == "buf0" || k == "buf1") {
     const size_t rows = static_cast<size_t>(n) * kTok;
-    join_rows_kernel<<<static_cast<unsigned>((rows * kC + 255) / 256), 256, 0, st>>>(h->ybuf[k == "buf1"], d_dst, rows);
+    join_rows_kernel<<<static_cast<unsigned>((rows * kC + 255) / 256), 256, 0, st>>>(h->ybuf[k == "buf1"], d_dst, rows,
+                                                                                     h->ybuf_fp8lo[k == "buf1"]);
     return check_launch(h, "join_rows_kernel");
   } else if (k == "q0" || k == "q1") { src = h->q[k == "q1"]; count = static_cast<size_t>(n) * kPooled * kC; }
   else if (k == "mpi0" || k == "mpi1") { src = h->mpi[k == "mpi1"]; count = static_cast<size_t>(n) * kPatches; }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace gnm {
@@ -18,8 +19,19 @@ constexpr int kPatchLen = 4;      // IGLOO patch size                  (referenc
 constexpr int kPool     = 8;      // max-pool size                     (reference model.py:23)
 constexpr int kPooled   = 749;    // 5997 // 8                         (reference igloo.py:164)
 constexpr int kHidden   = 512;    // dense width                       (reference model.py:28,40)
-constexpr int kRowHalfs = 256;    // activation row: 128 fp16 "hi" + 128 fp16 "lo"
 constexpr float kLeaky  = 0.1f;   // LeakyReLU slope                   (reference igloo.py:48,67)
+
+// Activation row in HBM: 768 bytes per position.  With Y = 32 * y (kActScale keeps the fp16 "lo" part and the fp8
+// planes away from their subnormal ranges; |y| may reach 2047 before fp16 overflows):
+//   [  0,256)  hi16 = fp16(Y)                       128 halves   -- main tensor-core operand, w_v, patch gather
+//   [256,512)  lo16 = fp16(Y - hi16)                128 halves   -- w_v 3-pass split, patch gather
+//   [512,640)  lo8  = e4m3((Y - hi16) * 128)        128 bytes    -- conv correction pass  lo(A) * hi(W)
+//   [640,768)  hi8  = e4m3(hi16 * 4)                128 bytes    -- conv correction pass  hi(A) * lo(W)
+constexpr int kRowBytes  = 768;
+constexpr int kOffHi16   = 0, kOffLo16 = 256, kOffLo8 = 512, kOffHi8 = 640;
+constexpr float kActScale = 32.f;          // 2^5
+constexpr float kLo8Scale = 128.f;         // lo8 = (Y - hi16) * 2^7   -> y_lo * 2^12
+constexpr float kHi8Scale = 4.f;           // hi8 = hi16 * 2^2         -> y_hi * 2^7
 
 // ----------------------------------------------------------------------------- small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -34,6 +46,11 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 }
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+
+// two floats -> two e4m3 bytes (round to nearest even, saturating)
+__device__ __forceinline__ uint16_t pack_e4m3x2(float a, float b) {
+  return static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3));
 }
 
 // error flag written by device-side timeouts (see mbar_wait); checked by the host API
@@ -128,6 +145,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with e4m3 operands (K = 32 per instruction); accumulates into the same fp32 TMEM accumulator
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrives on the mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -160,7 +185,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: A,B = fp16 (format 0), D = fp32, both K-major, dense.
+// kind::f16 instruction descriptor: A,B = fp16 (format 0), D = fp32, both K-major, dense.  The same bits serve
+// kind::f8f6f4 with e4m3 operands (format code 0 there too).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) |
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);

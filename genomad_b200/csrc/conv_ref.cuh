@@ -19,7 +19,7 @@ template <int kNTaps> constexpr int ref_smem_bytes() {
 // W: [kNTaps][128 in][128 out] fp32 (Keras layout).  kNTaps = 6 (conv) or 1 (w_v, no bias/act).
 template <int kNTaps, bool kBiasAct>
 __global__ void __launch_bounds__(kRefThreads)
-conv_ref_kernel(const __half* __restrict__ y_in, const float* __restrict__ W, const float* __restrict__ bias,
+conv_ref_kernel(const uint8_t* __restrict__ y_in, const float* __restrict__ W, const float* __restrict__ bias,
                 float* __restrict__ out_f32) {
   extern __shared__ float s_ref[];
   float* s_x = s_ref;                                   // [(32 + taps - 1)][128]
@@ -32,8 +32,9 @@ conv_ref_kernel(const __half* __restrict__ y_in, const float* __restrict__ W, co
     const int t = t0 - (kNTaps - 1) + r;
     float v = 0.f;
     if (t >= 0 && t < kTok) {
-      const __half* row = y_in + (static_cast<size_t>(w) * kTok + t) * kRowHalfs;
-      v = __half2float(row[c]) + __half2float(row[kC + c]);
+      const uint8_t* row = y_in + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
+      v = (__half2float(reinterpret_cast<const __half*>(row + kOffHi16)[c]) +
+           __half2float(reinterpret_cast<const __half*>(row + kOffLo16)[c])) * (1.f / kActScale);
     }
     s_x[i] = v;
   }
@@ -72,28 +73,38 @@ conv_ref_kernel(const __half* __restrict__ y_in, const float* __restrict__ W, co
   }
 }
 
-// fp32 rows -> fp16 hi|lo rows
-__global__ void split_rows_kernel(const float* __restrict__ in_f32, __half* __restrict__ y_out, size_t n_rows) {
+// fp32 rows -> activation rows (hi16 / lo16 planes only: the validation kernels never read the fp8 planes)
+__global__ void split_rows_kernel(const float* __restrict__ in_f32, uint8_t* __restrict__ y_out, size_t n_rows) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per (row, 4 channels)
   if (i >= n_rows * (kC / 4)) return;
   const size_t r = i / (kC / 4);
   const int c4 = static_cast<int>(i - r * (kC / 4));
   const float4 v = reinterpret_cast<const float4*>(in_f32)[i];
   __half h0, h1, h2, h3, l0, l1, l2, l3;
-  split_f16(v.x, h0, l0); split_f16(v.y, h1, l1); split_f16(v.z, h2, l2); split_f16(v.w, h3, l3);
-  __half* row = y_out + r * kRowHalfs;
-  *reinterpret_cast<uint2*>(row + c4 * 4) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-  *reinterpret_cast<uint2*>(row + kC + c4 * 4) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+  split_f16(kActScale * v.x, h0, l0); split_f16(kActScale * v.y, h1, l1);
+  split_f16(kActScale * v.z, h2, l2); split_f16(kActScale * v.w, h3, l3);
+  uint8_t* row = y_out + r * kRowBytes;
+  *reinterpret_cast<uint2*>(row + kOffHi16 + c4 * 8) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+  *reinterpret_cast<uint2*>(row + kOffLo16 + c4 * 8) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
 }
 
-// fp16 hi|lo rows -> fp32 rows (debug fetch)
-__global__ void join_rows_kernel(const __half* __restrict__ y_in, float* __restrict__ out_f32, size_t n_rows) {
+// activation rows -> fp32 rows (debug fetch): (hi16 + lo16) / 32, or (hi16 + lo8 / 128) / 32 for rows written by
+// conv2 (which stores only the planes conv3 reads)
+__global__ void join_rows_kernel(const uint8_t* __restrict__ y_in, float* __restrict__ out_f32, size_t n_rows, int fp8_lo) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_rows * kC) return;
   const size_t r = i / kC;
   const int c = static_cast<int>(i - r * kC);
-  const __half* row = y_in + r * kRowHalfs;
-  out_f32[i] = __half2float(row[c]) + __half2float(row[kC + c]);
+  const uint8_t* row = y_in + r * kRowBytes;
+  const float hi = __half2float(reinterpret_cast<const __half*>(row + kOffHi16)[c]);
+  float lo;
+  if (fp8_lo) {
+    const __half_raw hr = __nv_cvt_fp8_to_halfraw(row[kOffLo8 + c], __NV_E4M3);
+    lo = __half2float(__half(hr)) * (1.f / kLo8Scale);
+  } else {
+    lo = __half2float(reinterpret_cast<const __half*>(row + kOffLo16)[c]);
+  }
+  out_f32[i] = (hi + lo) * (1.f / kActScale);
 }
 
 // z[n][5997][128] -> q[n][749][128] = max over 8 consecutive positions (valid pooling)

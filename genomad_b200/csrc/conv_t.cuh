@@ -7,17 +7,25 @@
 //   y_proj = y @ w_v, MaxPool1D(8)  genomad/neural_network/igloo.py:208-210
 //         q[g,:] = max_{r<8} (y[8g+r,:] @ Wv)     g < 749 (positions 5992..5996 are dropped)
 //
-// Arithmetic: fp32-equivalent "3-pass split".  Every fp32 operand x is carried as two fp16 numbers
-// hi = fp16(x), lo = fp16(x - hi) (|x - hi - lo| <~ 2^-22 |x|).  A product A*B is evaluated on the
-// tensor cores as Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32 accumulation in TMEM (the dropped Alo*Blo
-// term is ~2^-22).  tools/precision_study.py (profiles/r01_precision_study.md) shows why a single
-// TF32/fp16 pass is not enough for the 1e-4 parity bar (1.4e-4 worst case for the convs, 7e-4 for w_v)
-// while this recipe gives ~7e-6.
+// Arithmetic: fp32-equivalent split.  Every operand x is carried as hi = fp16(x) plus a correction
+// lo = x - hi, and A*B is evaluated on the tensor cores as Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32
+// accumulation in ONE TMEM accumulator (the dropped Alo*Blo term is ~2^-22).  tools/precision_study.py
+// (profiles/r01_precision_study.md) shows why a single TF32/fp16 pass is not enough for the 1e-4 parity
+// bar (1.4e-4 worst case for the convs, 7e-4 for w_v).
+//   * w_v (feeds max-pool -> mean -> BatchNorm with a 31x gain): all three passes in fp16 (kind::f16), ~7e-6.
+//   * convs: the main pass Ahi*Bhi in fp16; the two correction passes only need ~8 bits, so they run in
+//     e4m3 (kind::f8f6f4, K = 32 per instruction: twice the rate) on pre-scaled operands.  All passes are
+//     scaled to a common 2^S so they add up in the same accumulator, and the epilogue multiplies by 2^-S:
+//         main  : (32*Ahi)            x fp16(Whi * 2^d)          S = 5 + d          (d = 16 for |W| < 0.78)
+//         corr1 : e4m3(Alo * 2^12)    x e4m3(Whi * 2^(S-12))
+//         corr2 : e4m3(Ahi * 2^7)     x e4m3(Wlo * 2^(S-7))
+//     CPU emulation of exactly this recipe: max |dp| 6.5e-6 over 256 worst-case-family windows.
 //
-// Data layout.  Activations are [n][5997][256] fp16 (128 "hi" | 128 "lo" halves per 512-byte row).
-// One work unit = 256 consecutive positions of one window (24 units per window).  For each
-// (plane, K-half) two TMA boxes of 136 rows x 64 channels bring rows t0-5 .. t0+266 of the window into
-// a 272-row SWIZZLE_128B slab ONCE; conv tap j is the same slab read j rows further down -- only the
+// Data layout.  Activation rows are 768 bytes: hi16 | lo16 | lo8 | hi8 (common.cuh), tensor [n][5997][768 B].
+// One work unit = 256 consecutive positions of one window (24 units per window).  The unit's operands
+// are four slab REGIONS of 272 rows x 128 bytes (conv: hi16 ch 0-63, hi16 ch 64-127, lo8, hi8;
+// w_v: hi16 and lo16 halves); two TMA boxes of 136 rows bring rows t0-5 .. t0+266 of the window into
+// each SWIZZLE_128B region ONCE; conv tap j is the same slab read j rows further down -- only the
 // UMMA descriptor start address changes (row j is position t0-5+j; TMA zero-fills rows with t < 0 or
 // t >= 5997, which is exactly Keras' causal padding).  Measured on B200 (profiles/r01_bringup.md): the
 // 128B swizzle is a function of the absolute shared-memory address, so a descriptor may start at any
@@ -31,12 +39,12 @@
 //
 //     D^T[cout (M=128 TMEM lanes)][position (N=256 TMEM columns)] += W_tap^T[cout][cin] * Y[position + tap][cin]
 //
-//   A operand = one 16 KB weight stage [128 cout][64 cin] fp16 K-major SWIZZLE_128B (streamed by TMA through
-//               a 4-stage ring, host-packed in consumption order), shared by both tiles of the unit;
-//   B operand = 256 consecutive rows of the activation slab.
+//   A operand = one 16 KB weight stage, [128 cout][64 cin] fp16 or [128 cout][128 cin] e4m3, K-major
+//               SWIZZLE_128B (streamed by TMA through a 4-stage ring, host-packed in consumption order);
+//   B operand = 256 consecutive rows of one slab region.
 //
-// Schedule.  Stages are ordered K-half-major (all taps of channels 0..63, then 64..127) so each half of
-// the slab is free after 12 stages and is reloaded for the NEXT unit while the other half is in use;
+// Schedule.  Weight stages are ordered region-major (all 6 taps against region 0, then region 1, ...) so a
+// region is free after its 6 stages and is reloaded for the NEXT unit while the other regions are in use;
 // activations and weights have separate producer threads; 2 accumulator sets x 256 TMEM columns let the
 // epilogue of unit u overlap the MMAs of unit u+1.  The MMA warp stays converged and issues through
 // elect.sync so consecutive tcgen05.mma stay on the uniform datapath (the first version issued from a
@@ -46,8 +54,9 @@
 //   warp 0 lane 0 : weight producer (TMA)          warp 3 lane 0 : activation producer (TMA)
 //   warp 1        : tcgen05.mma issuer             warp 2        : TMEM allocator
 //   warps 4..7    : epilogue.  A thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
-//       conv : bias + LeakyReLU + fp16 hi/lo split, transposed through a 16 KB shared staging tile
-//              ([32 positions][256 halves]) and written back as full 512-byte activation rows;
+//       conv : 2^-S scale + bias + LeakyReLU, then the planes the consumer needs (conv2 -> hi16, lo8, hi8 for
+//              conv3; conv3 -> hi16, lo16 for w_v / gather), transposed through a 16 KB shared staging tile
+//              ([32 positions][512 B]) and written back as two 256-byte segments per activation row;
 //       w_v  : the max over 8 consecutive positions is a max over 8 registers (no shuffles); a warp writes
 //              128 contiguous bytes of q[g][:] per pooled row.
 #pragma once
@@ -59,38 +68,45 @@ namespace gnm {
 constexpr int kTileM       = 128;
 constexpr int kUnitsPerWin = (kTok + 2 * kTileM - 1) / (2 * kTileM);   // 24
 constexpr int kSlabRows    = 136;                                // rows per TMA box
-constexpr int kARegion     = kSlabRows * 128;                    // bytes per box: rows x 128 B (64 fp16)  = 17408
+constexpr int kARegion     = kSlabRows * 128;                    // bytes per box: rows x 128 B            = 17408
 constexpr int kA2Region    = 2 * kARegion;                       // 272-row slab region                    = 34816
-constexpr int kA2Bytes     = 4 * kA2Region;                      // hi.k0 hi.k1 lo.k0 lo.k1                = 139264
-constexpr int kBStage      = 128 * 128;                          // one weight stage: 128 rows x 64 fp16   = 16384
+constexpr int kNumRegions  = 4;
+constexpr int kA2Bytes     = kNumRegions * kA2Region;            //                                        = 139264
+constexpr int kBStage      = 128 * 128;                          // one weight stage: 128 rows x 128 B     = 16384
 constexpr int kConvThreads = 256;
-constexpr int kConvStages  = 24;                                 // conv: (K-half, tap, weight hi/lo)
+constexpr int kConvStages  = 24;                                 // conv: (region, tap)
 constexpr int kWvStages    = 4;                                  // w_v : (K-half, weight hi/lo)
+constexpr int kTWStages    = 4;                                  // weight ring depth (16 KB each)
+constexpr int kTStageTile  = 32 * 512;                           // 16 KB epilogue staging tile
+constexpr int kConvTSmem   = kA2Bytes + kTWStages * kBStage + kTStageTile + 2048;
 
 struct ConvTcParams {
   const float* bias;        // [128] (conv) or nullptr (w_v)
-  __half* y_out;            // [n][5997][256] (conv) or nullptr
+  uint8_t* y_out;           // [n][5997][768 B] (conv) or nullptr
   float* q_out;             // [n][749][128] (w_v) or nullptr
+  float out_scale;          // conv: 2^-S (undoes the common operand scaling); w_v: 1/32 (activation scale)
+  int out_fp8;              // conv: 1 = write hi16 + lo8 + hi8 (consumer is a conv), 0 = write hi16 + lo16
   int n_tiles;              // number of work units = n_windows * 24
   int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores
   long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
   DeviceStatus* status;
 };
 
-constexpr int kTWStages   = 4;                                   // weight ring depth (16 KB each)
-constexpr int kTStageTile = 32 * kRowHalfs * 2;                  // 16 KB epilogue staging tile
-constexpr int kConvTSmem  = kA2Bytes + kTWStages * kBStage + kTStageTile + 2048;
-
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// byte offset inside the 768-byte activation row of the data that fills slab region r
+template <bool kWvMode> __device__ __forceinline__ constexpr int region_src(int r) {
+  return kWvMode ? (r == 0 ? kOffHi16 : r == 1 ? kOffHi16 + 128 : r == 2 ? kOffLo16 : kOffLo16 + 128)
+                 : (r == 0 ? kOffHi16 : r == 1 ? kOffHi16 + 128 : r == 2 ? kOffLo8 : kOffHi8);
 }
 
 template <bool kWvMode>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
               const ConvTcParams p) {
-  constexpr int kSPK = kWvMode ? 2 : 12;                          // stages per K-half
-  constexpr int kStagesU = 2 * kSPK;                              // stages per unit
+  constexpr int kStagesU = kWvMode ? kWvStages : kConvStages;     // stages per unit
   constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -98,13 +114,13 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
   uint8_t* s_w = smem + kA2Bytes;                        // weight ring
   uint8_t* s_stage = s_w + kTWStages * kBStage;          // epilogue staging tile (conv mode)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTStageTile);
-  uint64_t* a_full = bars;            // [2]  per K-half
-  uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* w_full = bars + 4;        // [4]
-  uint64_t* w_empty = bars + 8;       // [4]
-  uint64_t* acc_full = bars + 12;     // [2]
-  uint64_t* acc_empty = bars + 14;    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* a_full = bars;            // [4]  per region
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* w_full = bars + 8;        // [4]
+  uint64_t* w_empty = bars + 12;      // [4]
+  uint64_t* acc_full = bars + 16;     // [2]
+  uint64_t* acc_empty = bars + 18;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles;      // n_windows * 24
@@ -112,7 +128,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_act);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kNumRegions; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kTWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
@@ -134,16 +150,13 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       const int w = unit / kUnitsPerWin;
       const int t0 = (unit - w * kUnitsPerWin) * (2 * kTileM);
 #pragma unroll
-      for (int kh = 0; kh < 2; ++kh) {
-        mbar_wait(&a_empty[kh], ph ^ 1, p.status, 100 + kh);
-        mbar_arrive_expect_tx(&a_full[kh], 2 * kA2Region);
-#pragma unroll
-        for (int plane = 0; plane < 2; ++plane) {
-          uint8_t* dst = s_a + (plane * 2 + kh) * kA2Region;
-          const int c0 = plane * kC + kh * 64;
-          tma_load_3d(dst, &tm_act, &a_full[kh], c0, t0 - 5, w);
-          tma_load_3d(dst + kARegion, &tm_act, &a_full[kh], c0, t0 - 5 + kSlabRows, w);
-        }
+      for (int k = 0; k < kNumRegions; ++k) {
+        const int r = kWvMode ? (k == 0 ? 0 : k == 1 ? 2 : k == 2 ? 1 : 3) : k;      // order in which the MMAs need them
+        mbar_wait(&a_empty[r], ph ^ 1, p.status, 100 + r);
+        mbar_arrive_expect_tx(&a_full[r], kA2Region);
+        uint8_t* dst = s_a + r * kA2Region;
+        tma_load_3d(dst, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5, w);
+        tma_load_3d(dst + kARegion, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5 + kSlabRows, w);
       }
     }
   } else if (warp == 0 && lane == 0) {
@@ -176,9 +189,17 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 200 + as);
       w_acc += clock64() - tq;
       for (int q = 0; q < kStagesU; ++q, ++wcount) {
-        const int kh = q / kSPK, r = q - kh * kSPK;
-        const int tap = kWvMode ? 5 : (r >> 1), w_lo = r & 1;
-        if (r == 0) { tq = clock64(); mbar_wait(&a_full[kh], aph, p.status, 210 + kh); w_a += clock64() - tq; }
+        // conv: stage q = (region q/6, tap q%6); regions 0,1 are fp16 K-halves, 2 = lo8 (x Whi8), 3 = hi8 (x Wlo8)
+        // w_v : stage q = (K-half q/2, weight hi/lo q%2); hi-weight stages multiply both the hi16 and the lo16 region
+        const int reg = kWvMode ? (q >> 1) : (q / 6);
+        const int tap = kWvMode ? 5 : (q - reg * 6);
+        const bool first_use = kWvMode ? ((q & 1) == 0) : (tap == 0);
+        if (first_use) {
+          tq = clock64();
+          mbar_wait(&a_full[reg], aph, p.status, 210 + reg);
+          if (kWvMode) mbar_wait(&a_full[2 + reg], aph, p.status, 214 + reg);
+          w_a += clock64() - tq;
+        }
         const int s = wcount % kTWStages;
         const uint32_t wphase = (wcount / kTWStages) & 1;
         tq = clock64();
@@ -187,15 +208,31 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint64_t wdesc = desc0 + ((w_base + s * kBStage) >> 4);                              // A: weights
-          const uint64_t yhi = desc0 + ((a_base + kh * kA2Region + tap * 128) >> 4);                 // B: activations
-          const uint64_t ylo = desc0 + ((a_base + (2 + kh) * kA2Region + tap * 128) >> 4);
+          const uint64_t y0 = desc0 + ((a_base + reg * kA2Region + tap * 128) >> 4);                 // B: activations
+          if (kWvMode) {
+            const uint64_t y1 = desc0 + ((a_base + (2 + reg) * kA2Region + tap * 128) >> 4);        // lo16 region
+            const bool w_lo = (q & 1) != 0;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(acc, wdesc + kk * 2, yhi + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
-            if (!w_lo) umma_f16(acc, wdesc + kk * 2, ylo + kk * 2, kIdesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+              if (!w_lo) umma_f16(acc, wdesc + kk * 2, y1 + kk * 2, kIdesc, 1u);
+            }
+            umma_commit(&w_empty[s]);
+            if (q == 0) umma_commit(&a_empty[2]);                  // lo16.k0 is only used by stage 0
+            if (q == 1) umma_commit(&a_empty[0]);
+            if (q == 2) umma_commit(&a_empty[3]);
+            if (q == 3) umma_commit(&a_empty[1]);
+          } else {
+            if (reg < 2) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f8(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, 1u);
+            }
+            umma_commit(&w_empty[s]);
+            if (tap == 5) umma_commit(&a_empty[reg]);              // this region of the slab is no longer needed
           }
-          umma_commit(&w_empty[s]);
-          if (r == kSPK - 1) umma_commit(&a_empty[kh]);      // this K-half of the slab is no longer needed
           if (q == kStagesU - 1) umma_commit(&acc_full[as]);
         }
         __syncwarp();
@@ -210,7 +247,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
     const int wq = warp - 4;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
     const int ch = wq * 32 + lane;
     const float bias = kWvMode ? 0.f : p.bias[ch];
-    const int te = threadIdx.x - 128;                          // 0..127 within the epilogue group
+    const float oscale = p.out_scale;
     int it = 0;
     long long w_full_c = 0, tq;
     const long long t_begin = clock64();
@@ -238,33 +275,51 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
 #pragma unroll
             for (int k = 1; k < 8; ++k) m = fmaxf(m, __uint_as_float(r[8 * g + k]));
             const int gg = (p0 >> 3) + g;
-            if (gg < kPooled) p.q_out[(static_cast<size_t>(w) * kPooled + gg) * kC + ch] = m;
+            if (gg < kPooled) p.q_out[(static_cast<size_t>(w) * kPooled + gg) * kC + ch] = m * oscale;
           }
         } else {
+          // staging row (512 B): [hi16 x128 | lo16 x128]  or  [hi16 x128 | lo8 x128 | hi8 x128]
           __half* st_hi = reinterpret_cast<__half*>(s_stage) + ch;
-          __half* st_lo = st_hi + kC;
+          if (p.out_fp8) {
+            uint8_t* st_lo8 = s_stage + 256 + ch;
+            uint8_t* st_hi8 = s_stage + 384 + ch;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = lrelu(__uint_as_float(r[i]) + bias);
-            __half h, l;
-            split_f16(v, h, l);
-            st_hi[i * kRowHalfs] = h;
-            st_lo[i * kRowHalfs] = l;
+            for (int i = 0; i < 32; i += 2) {
+              const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
+              const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
+              const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+              const float f0 = __half2float(h0), f1 = __half2float(h1);
+              const uint16_t lo = pack_e4m3x2((y0 - f0) * kLo8Scale, (y1 - f1) * kLo8Scale);
+              const uint16_t hi = pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale);
+              st_hi[i * 256] = h0;            st_hi[(i + 1) * 256] = h1;             // row stride 512 B = 256 halves
+              st_lo8[i * 512] = lo & 0xff;    st_lo8[(i + 1) * 512] = lo >> 8;
+              st_hi8[i * 512] = hi & 0xff;    st_hi8[(i + 1) * 512] = hi >> 8;
+            }
+          } else {
+            __half* st_lo = st_hi + kC;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float y = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
+              __half h, l;
+              split_f16(y, h, l);
+              st_hi[i * 256] = h;
+              st_lo[i * 256] = l;
+            }
           }
           named_bar_sync(1, 128);                              // staging tile complete
-          // each warp writes back 8 full rows (512 B = 32 lanes x 16 B): perfectly coalesced
+          // each warp writes back 8 rows; a row leaves as two 256-byte segments (lanes 0-15 / 16-31)
           uint4 v[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            v[k] = *reinterpret_cast<const uint4*>(s_stage + (wq * 8 + k) * (kRowHalfs * 2) + lane * 16);
+            v[k] = *reinterpret_cast<const uint4*>(s_stage + (wq * 8 + k) * 512 + lane * 16);
           named_bar_sync(2, 128);                              // staging tile may be overwritten
           if (!(p.experiment & 2)) {
+            const int dst_off = lane < 16 ? kOffHi16 + lane * 16 : (p.out_fp8 ? kOffLo8 : kOffLo16) + (lane - 16) * 16;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int t = p0 + wq * 8 + k;
               if (t < kTok)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.y_out) +
-                                          (static_cast<size_t>(w) * kTok + t) * (kRowHalfs * 2) + lane * 16) = v[k];
+                *reinterpret_cast<uint4*>(p.y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes + dst_off) = v[k];
             }
           }
         }
@@ -277,7 +332,6 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       long long* d = p.dbg + blockIdx.x * 8;
       d[5] = clock64() - t_begin; d[6] = w_full_c;
     }
-    (void)te;
   }
 
   tc_fence_before();

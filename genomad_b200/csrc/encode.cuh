@@ -68,7 +68,7 @@ encode_tokens_kernel(const uint8_t* __restrict__ ascii, uint16_t* __restrict__ t
 // ------------------------------------------------------------------------------------------
 // K0+K1 fused: one CTA per (window, 256-position segment).  Tokens are computed into shared
 // memory (from ASCII, or copied from a token buffer), then one warp per position produces the
-// 128-channel activation row and writes it as fp16 hi | fp16 lo (256 halves = 512 B).
+// 128-channel activation row and writes its four planes (768 B, layout in common.cuh).
 //
 //   y1[t] = lrelu( (A + B) + bias ),   A = (W1[0][k0] + W1[1][k1]) + W1[2][k2],  B = (W1[3][k3] + W1[4][k4]) + W1[5][k5]
 //
@@ -89,7 +89,7 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
                    const float* __restrict__ table,   // [6][257][128]
                    const float* __restrict__ triple,  // [2][4096][128]: A-table, B-table
                    const float* __restrict__ bias,    // [128]
-                   __half* __restrict__ y_out,        // [n][5997][256]
+                   uint8_t* __restrict__ y_out,       // [n][5997][768 B] activation rows (hi16 | lo16 | lo8 | hi8)
                    int n_windows) {
   __shared__ int16_t s_tok[kEmbSeg + 8];    // s_tok[i] = token at position t0 - 5 + i, or -1 (causal pad)
   __shared__ uint8_t s_b[kEmbSeg + 16];
@@ -146,12 +146,21 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
       B = add4(add4(row(3, tk[3]), row(4, tk[4])), row(5, tk[5]));
     }
     float4 a = add4(A, B);
-    a.x = lrelu(a.x + b4.x); a.y = lrelu(a.y + b4.y); a.z = lrelu(a.z + b4.z); a.w = lrelu(a.w + b4.w);
+    // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
+    a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
+    a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
     __half h0, h1, h2, h3, l0, l1, l2, l3;
     split_f16(a.x, h0, l0); split_f16(a.y, h1, l1); split_f16(a.z, h2, l2); split_f16(a.w, h3, l3);
-    __half* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowHalfs;
-    *reinterpret_cast<uint2*>(rowp + lane * 4) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-    *reinterpret_cast<uint2*>(rowp + kC + lane * 4) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+    const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2), f3 = __half2float(h3);
+    uint8_t* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
+    *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+    *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+    *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
+        static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, (a.y - f1) * kLo8Scale)) |
+        (static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, (a.w - f3) * kLo8Scale)) << 16);
+    *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
+        static_cast<uint32_t>(pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale)) |
+        (static_cast<uint32_t>(pack_e4m3x2(f2 * kHi8Scale, f3 * kHi8Scale)) << 16);
   }
 }
 

@@ -41,9 +41,9 @@ constexpr int kGsDepth = 4;                                      // windows in f
 static_assert(kGsSlots >= kPatches * kPatchLen, "not enough entry slots");
 
 __global__ void __launch_bounds__(kGsThreads, 3)
-patch_stream_kernel(const __half* __restrict__ y,          // [n][5997][256]
+patch_stream_kernel(const uint8_t* __restrict__ y,         // [n][5997][768 B]; reads the hi16 / lo16 planes (scaled by 32)
                     const int32_t* __restrict__ ent_pos,   // [8880] position of each slot (0 for padding)
-                    const float* __restrict__ ent_w,       // [8880][128] folded weights of each slot (0 for padding)
+                    const float* __restrict__ ent_w,       // [8880][128] folded weights / 32 of each slot (0 for padding)
                     float* __restrict__ part,              // [n][8880]
                     int n_windows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -53,14 +53,14 @@ patch_stream_kernel(const __half* __restrict__ y,          // [n][5997][256]
   float wt[kGsPerWarp][8];
 #pragma unroll
   for (int i = 0; i < kGsPerWarp; ++i) {
-    rowoff[i] = ent_pos[e0 + i] * (kRowHalfs * 2) + half * (kC * 2) + l16 * 16;
+    rowoff[i] = ent_pos[e0 + i] * kRowBytes + (half ? kOffLo16 : kOffHi16) + l16 * 16;
     const float4 a = *reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(e0 + i) * kC + l16 * 8);
     const float4 b = *reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(e0 + i) * kC + l16 * 8 + 4);
     wt[i][0] = a.x; wt[i][1] = a.y; wt[i][2] = a.z; wt[i][3] = a.w;
     wt[i][4] = b.x; wt[i][5] = b.y; wt[i][6] = b.z; wt[i][7] = b.w;
   }
-  const uint8_t* ybase = reinterpret_cast<const uint8_t*>(y);
-  constexpr size_t kWinBytes = static_cast<size_t>(kTok) * kRowHalfs * 2;
+  const uint8_t* ybase = y;
+  constexpr size_t kWinBytes = static_cast<size_t>(kTok) * kRowBytes;
   uint4 ring[kGsDepth][kGsPerWarp];
 #pragma unroll
   for (int d = 0; d < kGsDepth; ++d)

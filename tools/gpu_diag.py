@@ -76,7 +76,7 @@ def run_one(impl, mode, wkind, n):
 
     clf.set_option("debug_stop", 2)
     clf.predict_ascii(da); torch.cuda.synchronize()
-    ok &= maxdiff("y2 (conv2)", clf.debug_fetch("buf1", n).cpu().numpy(), inter["y2"].numpy(), 8e-6)
+    ok &= maxdiff("y2 (conv2)", clf.debug_fetch("buf1", n).cpu().numpy(), inter["y2"].numpy(), 6e-5)
     ok &= maxdiff("q0 (w_v0 + maxpool on y1)", clf.debug_fetch("q0", n).cpu().numpy(), inter["ig0"]["q"].numpy(), 3e-6)
 
     clf.set_option("debug_stop", 3)
