@@ -48,6 +48,14 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
 
+// Packed fp32 -> (hi, lo) fp16 split of two values: one F2FP pack for hi, one unpack, one F2FP pack for lo
+// (the scalar F2F conversions run on the slow conversion pipe: 16/clk/SM).
+__device__ __forceinline__ void split2_f16(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hi);
+  lo = __floats2half2_rn(a - f.x, b - f.y);
+}
+
 // two floats -> two e4m3 bytes (round to nearest even, saturating)
 __device__ __forceinline__ uint16_t pack_e4m3x2(float a, float b) {
   return static_cast<uint16_t>(__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3));

@@ -287,23 +287,24 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
             for (int i = 0; i < 32; i += 2) {
               const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
               const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
-              const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
-              const float f0 = __half2float(h0), f1 = __half2float(h1);
-              const uint16_t lo = pack_e4m3x2((y0 - f0) * kLo8Scale, (y1 - f1) * kLo8Scale);
-              const uint16_t hi = pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale);
-              st_hi[i * 256] = h0;            st_hi[(i + 1) * 256] = h1;             // row stride 512 B = 256 halves
+              const __half2 h = __floats2half2_rn(y0, y1);
+              const float2 f = __half22float2(h);
+              const uint16_t lo = pack_e4m3x2((y0 - f.x) * kLo8Scale, (y1 - f.y) * kLo8Scale);
+              const uint16_t hi = pack_e4m3x2(f.x * kHi8Scale, f.y * kHi8Scale);
+              st_hi[i * 256] = __low2half(h); st_hi[(i + 1) * 256] = __high2half(h);   // row stride 512 B = 256 halves
               st_lo8[i * 512] = lo & 0xff;    st_lo8[(i + 1) * 512] = lo >> 8;
               st_hi8[i * 512] = hi & 0xff;    st_hi8[(i + 1) * 512] = hi >> 8;
             }
           } else {
             __half* st_lo = st_hi + kC;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float y = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
-              __half h, l;
-              split_f16(y, h, l);
-              st_hi[i * 256] = h;
-              st_lo[i * 256] = l;
+            for (int i = 0; i < 32; i += 2) {
+              const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
+              const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
+              __half2 h, l;
+              split2_f16(y0, y1, h, l);
+              st_hi[i * 256] = __low2half(h); st_hi[(i + 1) * 256] = __high2half(h);
+              st_lo[i * 256] = __low2half(l); st_lo[(i + 1) * 256] = __high2half(l);
             }
           }
           named_bar_sync(1, 128);                              // staging tile complete

@@ -149,12 +149,16 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
     // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
     a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
     a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
-    __half h0, h1, h2, h3, l0, l1, l2, l3;
-    split_f16(a.x, h0, l0); split_f16(a.y, h1, l1); split_f16(a.z, h2, l2); split_f16(a.w, h3, l3);
-    const float f0 = __half2float(h0), f1 = __half2float(h1), f2 = __half2float(h2), f3 = __half2float(h3);
+    __half2 h01, h23, l01, l23;
+    split2_f16(a.x, a.y, h01, l01);
+    split2_f16(a.z, a.w, h23, l23);
+    const float2 fa = __half22float2(h01), fb = __half22float2(h23);
+    const float f0 = fa.x, f1 = fa.y, f2 = fb.x, f3 = fb.y;
     uint8_t* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
-    *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-    *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+    *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
     *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
         static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, (a.y - f1) * kLo8Scale)) |
         (static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, (a.w - f3) * kLo8Scale)) << 16);

@@ -123,7 +123,7 @@ def test_stagewise_parity_synthetic(clf_syn, shipped):
         close("y2", clf_syn.debug_fetch("buf1", 8), it["y2"], 6e-5)      # stored as hi16 + e4m3 correction (what conv3 reads)
         close("q0", clf_syn.debug_fetch("q0", 8), it["ig0"]["q"], 1e-5)
         clf_syn.set_option("debug_stop", 3); clf_syn.predict_ascii(da); torch.cuda.synchronize()
-        close("y3", clf_syn.debug_fetch("buf0", 8), it["y3"], 1e-5)
+        close("y3", clf_syn.debug_fetch("buf0", 8), it["y3"], 2e-5)
     finally:
         clf_syn.set_option("debug_stop", 0)
     clf_syn.predict_ascii(da); torch.cuda.synchronize()
