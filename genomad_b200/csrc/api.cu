@@ -368,7 +368,8 @@ static int launch_conv(gnm_handle* h, int layer, int in_buf, int n, cudaStream_t
   p.n_tiles = n * kUnitsPerWin;                  // 256-position units
   p.status = h->status;
   p.experiment = h->conv_experiment;
-  p.dbg = (h->conv_experiment & 4) ? h->conv_dbg : nullptr;
+  // bit 4: cycle counters of conv3 (layer 1); bit 8: of conv2 (layer 0)
+  p.dbg = ((h->conv_experiment & 4) && layer == 1) || ((h->conv_experiment & 8) && layer == 0) ? h->conv_dbg : nullptr;
   p.bias = h->conv_bias[layer];
   p.y_out = h->ybuf[1 - in_buf];
   p.q_out = nullptr;

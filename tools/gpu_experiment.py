@@ -27,11 +27,12 @@ for exp in [int(x) for x in (sys.argv[1:] or ["0", "2"])]:
     clf.set_option("profile_stages", 0)
     print(f"experiment={exp}: " + "  ".join(f"{k}={sum(v)/len(v):.3f}" for k, v in acc.items()), flush=True)
 
-# cycle breakdown of the MMA issuer / epilogue (experiment bit 4)
-clf.set_option("conv_experiment", 4)
-clf.predict_ascii(a, out); torch.cuda.synchronize()
-d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
-names = ["mma_total", "mma_wait_acc_empty", "mma_wait_a_full", "mma_wait_b_full", "units", "epi_total", "epi_wait_acc_full"]
-print("conv_t cycle breakdown (mean over CTAs, last conv launch = conv3):")
-for i, nm in enumerate(names):
-    print(f"   {nm:22s} {d[:, i].mean():12.0f}  (per unit {d[:, i].mean() / max(d[:, 4].mean(), 1):9.0f})")
+# cycle breakdown of the MMA issuer / epilogue (experiment bit 4 = conv3, bit 8 = conv2)
+names = ["mma_total", "mma_wait_acc_empty", "mma_wait_a_full", "mma_wait_w_full", "units", "epi_total", "epi_wait_acc_full"]
+for bit, label in ((8, "conv2"), (4, "conv3")):
+    clf.set_option("conv_experiment", bit)
+    clf.predict_ascii(a, out); torch.cuda.synchronize()
+    d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
+    print(f"conv_t cycle breakdown, {label} (mean over CTAs):")
+    for i, nm in enumerate(names):
+        print(f"   {nm:22s} {d[:, i].mean():12.0f}  (per unit {d[:, i].mean() / max(d[:, 4].mean(), 1):9.0f})")
