@@ -55,8 +55,11 @@
 //   warp 1        : tcgen05.mma issuer             warp 2        : TMEM allocator
 //   warps 4..7    : epilogue.  A thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
 //       conv : 2^-S scale + bias + LeakyReLU, then the planes the consumer needs (conv2 -> hi16, lo8, hi8 for
-//              conv3; conv3 -> hi16, lo16 for w_v / gather), transposed through a 16 KB shared staging tile
-//              ([32 positions][512 B]) and written back as two 256-byte segments per activation row;
+//              conv3; conv3 -> hi16, lo16 for w_v / gather) stored straight to global memory: for a fixed position
+//              a warp's 32 lanes are 32 consecutive channels = one contiguous 64-byte (fp8: 32-byte) piece of the row
+//              (an earlier version transposed through a 16 KB shared staging tile; shared-memory bandwidth is the
+//              scarce resource of this kernel, and dropping the tile also paid for a 5th weight stage; a lane-pair
+//              exchange that halves the store count was measured and brought nothing);
 //       w_v  : the max over 8 consecutive positions is a max over 8 registers (no shuffles); a warp writes
 //              128 contiguous bytes of q[g][:] per pooled row.
 #pragma once
@@ -76,9 +79,8 @@ constexpr int kBStage      = 128 * 128;                          // one weight s
 constexpr int kConvThreads = 256;
 constexpr int kConvStages  = 24;                                 // conv: (region, tap)
 constexpr int kWvStages    = 4;                                  // w_v : (K-half, weight hi/lo)
-constexpr int kTWStages    = 4;                                  // weight ring depth (16 KB each)
-constexpr int kTStageTile  = 32 * 512;                           // 16 KB epilogue staging tile
-constexpr int kConvTSmem   = kA2Bytes + kTWStages * kBStage + kTStageTile + 2048;
+constexpr int kTWStages    = 5;                                  // weight ring depth (16 KB each)
+constexpr int kConvTSmem   = kA2Bytes + kTWStages * kBStage + 2048;
 
 struct ConvTcParams {
   const float* bias;        // [128] (conv) or nullptr (w_v)
@@ -91,10 +93,6 @@ struct ConvTcParams {
   long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
   DeviceStatus* status;
 };
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // byte offset inside the 768-byte activation row of the data that fills slab region r
 template <bool kWvMode> __device__ __forceinline__ constexpr int region_src(int r) {
@@ -112,15 +110,14 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_a = smem;                                   // activation slab: 4 regions x 272 rows x 128 B
   uint8_t* s_w = smem + kA2Bytes;                        // weight ring
-  uint8_t* s_stage = s_w + kTWStages * kBStage;          // epilogue staging tile (conv mode)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + kTStageTile);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kTWStages * kBStage);
   uint64_t* a_full = bars;            // [4]  per region
   uint64_t* a_empty = bars + 4;       // [4]
-  uint64_t* w_full = bars + 8;        // [4]
-  uint64_t* w_empty = bars + 12;      // [4]
-  uint64_t* acc_full = bars + 16;     // [2]
-  uint64_t* acc_empty = bars + 18;    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w_full = bars + 8;        // [5]
+  uint64_t* w_empty = bars + 13;      // [5]
+  uint64_t* acc_full = bars + 18;     // [2]
+  uint64_t* acc_empty = bars + 20;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_tiles;      // n_windows * 24
@@ -145,6 +142,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
   if (warp == 3 && lane == 0) {
     // ===================================================================== activation producer
     int it = 0;
+    const uint64_t pol = l2_policy_evict_first();          // activations stream through L2 once
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const int w = unit / kUnitsPerWin;
@@ -155,20 +153,21 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
         mbar_wait(&a_empty[r], ph ^ 1, p.status, 100 + r);
         mbar_arrive_expect_tx(&a_full[r], kA2Region);
         uint8_t* dst = s_a + r * kA2Region;
-        tma_load_3d(dst, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5, w);
-        tma_load_3d(dst + kARegion, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5 + kSlabRows, w);
+        tma_load_3d_hint(dst, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5, w, pol);
+        tma_load_3d_hint(dst + kARegion, &tm_act, &a_full[r], region_src<kWvMode>(r), t0 - 5 + kSlabRows, w, pol);
       }
     }
   } else if (warp == 0 && lane == 0) {
     // ===================================================================== weight producer
     uint32_t wcount = 0;
+    const uint64_t pol = l2_policy_evict_last();           // the 384 KB of weights are re-read by every CTA for every unit
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       for (int q = 0; q < kStagesU; ++q, ++wcount) {
         const int s = wcount % kTWStages;
         const uint32_t wphase = (wcount / kTWStages) & 1;
         mbar_wait(&w_empty[s], wphase ^ 1, p.status, 110 + s);
         mbar_arrive_expect_tx(&w_full[s], kBStage);
-        tma_load_2d(s_w + s * kBStage, &tm_w, &w_full[s], 0, q * 128);
+        tma_load_2d_hint(s_w + s * kBStage, &tm_w, &w_full[s], 0, q * 128, pol);
       }
     }
   } else if (warp == 1) {
@@ -278,11 +277,12 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
             if (gg < kPooled) p.q_out[(static_cast<size_t>(w) * kPooled + gg) * kC + ch] = m * oscale;
           }
         } else {
-          // staging row (512 B): [hi16 x128 | lo16 x128]  or  [hi16 x128 | lo8 x128 | hi8 x128]
-          __half* st_hi = reinterpret_cast<__half*>(s_stage) + ch;
+          // Direct global stores: for a fixed position the 32 lanes of a warp hold 32 consecutive channels, so one
+          // 2-byte store per lane is a contiguous 64-byte piece of the row (32 bytes for an fp8 plane).  No shared-memory
+          // staging: the MMAs already use ~75 % of the shared-memory bandwidth for their operands and TMA fills ~23 %.
+          uint8_t* rowp = p.y_out + (static_cast<size_t>(w) * kTok + p0) * kRowBytes;
+          const bool store = !(p.experiment & 2);
           if (p.out_fp8) {
-            uint8_t* st_lo8 = s_stage + 256 + ch;
-            uint8_t* st_hi8 = s_stage + 384 + ch;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
@@ -291,36 +291,36 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
               const float2 f = __half22float2(h);
               const uint16_t lo = pack_e4m3x2((y0 - f.x) * kLo8Scale, (y1 - f.y) * kLo8Scale);
               const uint16_t hi = pack_e4m3x2(f.x * kHi8Scale, f.y * kHi8Scale);
-              st_hi[i * 256] = __low2half(h); st_hi[(i + 1) * 256] = __high2half(h);   // row stride 512 B = 256 halves
-              st_lo8[i * 512] = lo & 0xff;    st_lo8[(i + 1) * 512] = lo >> 8;
-              st_hi8[i * 512] = hi & 0xff;    st_hi8[(i + 1) * 512] = hi >> 8;
+              if (store && p0 + i < kTok) {
+                uint8_t* q = rowp + i * kRowBytes;
+                reinterpret_cast<__half*>(q + kOffHi16)[ch] = __low2half(h);
+                q[kOffLo8 + ch] = static_cast<uint8_t>(lo & 0xff);
+                q[kOffHi8 + ch] = static_cast<uint8_t>(hi & 0xff);
+              }
+              if (store && p0 + i + 1 < kTok) {
+                uint8_t* q = rowp + (i + 1) * kRowBytes;
+                reinterpret_cast<__half*>(q + kOffHi16)[ch] = __high2half(h);
+                q[kOffLo8 + ch] = static_cast<uint8_t>(lo >> 8);
+                q[kOffHi8 + ch] = static_cast<uint8_t>(hi >> 8);
+              }
             }
           } else {
-            __half* st_lo = st_hi + kC;
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
               const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
               __half2 h, l;
               split2_f16(y0, y1, h, l);
-              st_hi[i * 256] = __low2half(h); st_hi[(i + 1) * 256] = __high2half(h);
-              st_lo[i * 256] = __low2half(l); st_lo[(i + 1) * 256] = __high2half(l);
-            }
-          }
-          named_bar_sync(1, 128);                              // staging tile complete
-          // each warp writes back 8 rows; a row leaves as two 256-byte segments (lanes 0-15 / 16-31)
-          uint4 v[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            v[k] = *reinterpret_cast<const uint4*>(s_stage + (wq * 8 + k) * 512 + lane * 16);
-          named_bar_sync(2, 128);                              // staging tile may be overwritten
-          if (!(p.experiment & 2)) {
-            const int dst_off = lane < 16 ? kOffHi16 + lane * 16 : (p.out_fp8 ? kOffLo8 : kOffLo16) + (lane - 16) * 16;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int t = p0 + wq * 8 + k;
-              if (t < kTok)
-                *reinterpret_cast<uint4*>(p.y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes + dst_off) = v[k];
+              if (store && p0 + i < kTok) {
+                uint8_t* q = rowp + i * kRowBytes;
+                reinterpret_cast<__half*>(q + kOffHi16)[ch] = __low2half(h);
+                reinterpret_cast<__half*>(q + kOffLo16)[ch] = __low2half(l);
+              }
+              if (store && p0 + i + 1 < kTok) {
+                uint8_t* q = rowp + (i + 1) * kRowBytes;
+                reinterpret_cast<__half*>(q + kOffHi16)[ch] = __high2half(h);
+                reinterpret_cast<__half*>(q + kOffLo16)[ch] = __high2half(l);
+              }
             }
           }
         }
