@@ -225,3 +225,23 @@ def test_cli_config1_end_to_end(tmp_path, shipped):
     for line, name, row in zip(lines[1:], names, ref):
         f = line.split("\t")
         assert f[0] == name and all(abs(float(x) - y) <= TOL + 5e-5 for x, y in zip(f[1:], row))
+
+
+def test_conv_operand_scaling_rule(shipped):
+    """The per-layer operand scaling chosen in gnm_create (conv_t.cuh): conv2 weights x4 (|W| > 0.78 -> smaller 2^d),
+    conv3 weights / 4 (small weights in the e4m3 planes).  The network function changes, so compare with the oracle
+    evaluated on the same modified weights."""
+    from genomad_b200 import engine
+    w = dict(shipped)
+    w["c2w"] = (shipped["c2w"] * 4).astype(np.float32)
+    w["c3w"] = (shipped["c3w"] / 4).astype(np.float32)
+    a = _families(24, seed=9)
+    tok = T.tokenize_windows(a)
+    ref = _oracle_probs(tok, w)
+    c = engine.Classifier(w, device=0, max_batch=32)
+    try:
+        p = c.predict_ascii(torch.from_numpy(a).cuda()).cpu().numpy()
+    finally:
+        c.close()
+    assert np.abs(p - ref).max() <= TOL
+    assert np.array_equal(p.argmax(1), ref.argmax(1))
