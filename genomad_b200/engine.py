@@ -109,7 +109,7 @@ class Classifier:
 
     weights : dict from genomad_b200.weights.load_weights() (short names -> numpy arrays in Keras layouts)
     device  : CUDA device index
-    max_batch : windows per internal step (workspace ~6.9 MB per window)
+    max_batch : windows per internal step (workspace ~10 MB per window)
     """
 
     def __init__(self, weights: Optional[Dict[str, np.ndarray]] = None, device: int = 0, max_batch: int = 1024):

@@ -318,3 +318,41 @@ def test_native_fasta_check_and_gzip(tmp_path):
     out = np.zeros((4, 6000), np.uint8)
     enc2 = sequence.ParsedFasta(g).encode(out)
     assert enc2.windows.base is out or np.shares_memory(enc2.windows, out)
+
+
+def test_native_fasta_property_random_texts(tmp_path):
+    """Property test: random FASTA-like texts (odd line breaks, N runs, lower case, junk, '>' inside lines) -- the native
+    reader, the Python statement and the oracle's transcription of the reference reader must agree exactly."""
+    from hypothesis import given, settings, strategies as st
+
+    alphabet = "ACGTNnacgtRY>- \t"
+    line = st.text(alphabet=alphabet, min_size=0, max_size=90)
+    rec = st.tuples(st.text(alphabet="abcXYZ_01 \t|", min_size=1, max_size=12), st.lists(line, min_size=0, max_size=6),
+                    st.integers(0, 3))
+    texts = st.tuples(st.lists(line, max_size=2), st.lists(rec, min_size=0, max_size=6), st.sampled_from(["\n", "\r\n", "\r"]))
+
+    @settings(max_examples=150, deadline=None)
+    @given(texts)
+    def check(t):
+        junk, recs, eol = t
+        parts = [ln.lstrip(">") for ln in junk]
+        for name, lines, big in recs:
+            if not name.split():
+                name = "x" + name
+            parts.append(">" + name)
+            parts += [ln.lstrip(">") for ln in lines]          # a body line starting with '>' would be a header
+            if big:
+                parts.append("ACGTNACGT" * (300 * big))       # enough sequence for several windows sometimes
+        text = eol.join(parts) + (eol if parts else "")
+        p = tmp_path / "h.fna"
+        p.write_text(text, newline="")
+        a = sequence.encode_fasta(p)
+        b = sequence.encode_fasta_py(p)
+        names, ids, ascii_arr, _ = T.encode_fasta(p)
+        assert list(a.names) == list(b.names) == list(names)
+        assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.contig_ids, ids)
+        assert np.array_equal(a.windows, b.windows) and np.array_equal(a.windows, ascii_arr)
+        pf = sequence.ParsedFasta(p)
+        assert pf.check() == sequence.check_fasta(p)
+
+    check()
