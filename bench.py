@@ -66,7 +66,7 @@ def synth_windows(n: int, seed: int, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -177,7 +177,7 @@ def run_reference_arm(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -303,6 +303,16 @@ def main():
                          "note": "algorithmic FLOPs (one pass). The kernel executes one fp16 pass plus two e4m3 correction "
                                  "passes at twice the rate = 2 pass-units of tensor time, so frac is bounded by 0.5; "
                                  "bf16_equivalent_tflops = 2 x achieved is the figure comparable with the bf16 peak"},
+            # HBM-bound stages against the measured copy bandwidth (algorithmic bytes per launch / launch time)
+            "rooflines_hbm": {
+                name: {"bound": "hbm", "achieved": gb / (stage_ms[key] * 1e-3) if stage_ms.get(key) else None,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": gb / (stage_ms[key] * 1e-3) / peaks["hbm_gbs"] if stage_ms.get(key) else None,
+                       "algorithmic_gbytes_per_launch": gb}
+                for name, key, gb in (
+                    ("patch_stream_kernel (IGLOO patch gather, 8400 rows x 512 B per window)", "gather1", B * 4300800 / 1e9),
+                    ("conv_t_kernel<true> (w_v + max-pool: reads hi16+lo16 planes once)", "wv1", B * (5997 * 512 + 749 * 512) / 1e9),
+                    ("embed_conv1_kernel (encode + layer 1: writes four planes)", "embed_conv1", B * (6000 + 5997 * 768) / 1e9))},
             "stage_ms": stage_ms,
             "model_tflops_algorithmic": B * FLOP_DENSE_TOTAL / (total_ms / K * 1e-3) / 1e12,
         }
