@@ -71,7 +71,7 @@ struct gnm_handle {
   float* q[2] = {nullptr, nullptr};
   float* mpi[2] = {nullptr, nullptr};
   float* part = nullptr;                             // [max_batch][8880] per-entry partial dot products
-  float* logits = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
+  float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
   float* out_stage[2] = {nullptr, nullptr};
@@ -300,6 +300,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   GNM_CUDA(cudaMemset(h->conv_dbg, 0, static_cast<size_t>(h->num_sms) * 8 * sizeof(long long)));
   if (dev_alloc(h, &h->part, mb * kGsSlots)) return 1;
   if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
+  if (dev_alloc(h, &h->logits_part, mb * kLogitsLd * 4)) return 1;
   if (dev_alloc(h, &h->h0, mb * 256)) return 1;
   if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
   if (dev_alloc(h, &h->h2, mb * kHidden)) return 1;
@@ -435,12 +436,27 @@ static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, 
   const int nb = (N + kGemmBN - 1) / kGemmBN;
   if (M >= 64) {                                           // 32-row tiles only for tiny batches (measured slower otherwise)
     dim3 grid(nb, (M + 63) / 64);
-    sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+    sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu, K);
   } else {
     dim3 grid(nb, (M + 31) / 32);
-    sgemm_epi_kernel<32><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu);
+    sgemm_epi_kernel<32><<<grid, 128, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, scale, shift, relu, K);
   }
   return check_launch(h, "sgemm_epi_kernel");
+}
+
+// logits = mpi @ w_qk: M = n windows is small (192 tiles of 64x64 at batch 1024), so K = 2100 is split 4 ways to put
+// ~5 CTAs on every SM; the partials are summed in fixed order by splitk_reduce_kernel.
+constexpr int kLogitsSplit = 4;
+static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
+  const int k_chunk = ((kPatches + kLogitsSplit - 1) / kLogitsSplit + kGemmBK - 1) / kGemmBK * kGemmBK;   // 528
+  dim3 grid((kPooled + kGemmBN - 1) / kGemmBN, (n + 63) / 64, kLogitsSplit);
+  sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(h->mpi[s], kPatches, h->wqk[s], kPooled, h->logits_part, kLogitsLd, n, kPooled,
+                                            kPatches, nullptr, nullptr, nullptr, 0, k_chunk);
+  if (check_launch(h, "sgemm_epi_kernel(split-K)")) return 1;
+  const size_t total = static_cast<size_t>(n) * kLogitsLd;
+  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(h->logits_part, h->logits, n, kLogitsLd,
+                                                                                    kPooled, kLogitsSplit);
+  return check_launch(h, "splitk_reduce_kernel");
 }
 
 // One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
@@ -485,8 +501,7 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   if (launch_gather(h, 1, 0, n, st)) return 1;
   for (int s = 0; s < 2; ++s) {
     timer_mark(h, s ? "logits1" : "logits0", st);
-    if (launch_sgemm(h, h->mpi[s], kPatches, h->wqk[s], kPooled, h->logits, kLogitsLd, n, kPooled, kPatches, nullptr,
-                     nullptr, nullptr, 0, st)) return 1;
+    if (launch_logits(h, s, n, st)) return 1;
     timer_mark(h, s ? "attention1" : "attention0", st);
     attention_kernel<<<n, 128, 0, st>>>(h->logits, h->q[s], h->h0, s * kC);
     if (check_launch(h, "attention_kernel")) return 1;

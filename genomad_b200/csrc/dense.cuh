@@ -26,8 +26,13 @@ __global__ void __launch_bounds__(kBM * 4)
 sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
-                 const float* __restrict__ shift, int relu) {
+                 const float* __restrict__ shift, int relu, int k_chunk) {
+  // split-K: blockIdx.z owns k in [z*k_chunk, (z+1)*k_chunk) and writes its partial product to C + z*M*ldc (the caller
+  // passes bias/scale = nullptr then and finishes with splitk_reduce_kernel); k_chunk >= K means no split.
   constexpr int kThreads = kBM * 4;
+  const int k_lo = blockIdx.z * k_chunk;
+  const int k_hi = min(K, k_lo + k_chunk);
+  C += static_cast<size_t>(blockIdx.z) * M * ldc;
   __shared__ float s_a[kGemmBK][kBM + 4];
   __shared__ float s_b[kGemmBK][kGemmBN + 4];
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kGemmBN;
@@ -37,14 +42,14 @@ sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kGemmBK) {
+  for (int k0 = k_lo; k0 < k_hi; k0 += kGemmBK) {
     {   // A tile: kBM rows x 16 k  (thread -> row = tid/4, 4 consecutive k)
       const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) * 4;
       const int gm = m0 + r;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int gk = k0 + kk + i;
-        s_a[kk + i][r] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
+        s_a[kk + i][r] = (gm < M && gk < k_hi) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
       }
     }
     // B tile: 16 k x 64 cols, 4 consecutive cols per slot
@@ -54,7 +59,7 @@ sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int gn = n0 + c + i;
-        s_b[kk][c + i] = (gk < K && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
+        s_b[kk][c + i] = (gk < k_hi && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
       }
     }
     __syncthreads();
@@ -87,6 +92,17 @@ sgemm_epi_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       C[static_cast<size_t>(gm) * ldc + gn] = v;
     }
   }
+}
+
+// C[m][n] = ((P0 + P1) + P2) + ... over `parts` split-K partials, added in fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partials, float* __restrict__ C, int M, int ldc, int N, int parts) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(M) * ldc;
+  if (i >= total || static_cast<int>(i % ldc) >= N) return;
+  float v = partials[i];
+  for (int z = 1; z < parts; ++z) v += partials[static_cast<size_t>(z) * total + i];
+  C[i] = v;
 }
 
 // Dense(512 -> 3) + softmax: one warp per window.
