@@ -50,10 +50,10 @@
 // elect.sync so consecutive tcgen05.mma stay on the uniform datapath (the first version issued from a
 // divergent single lane and spent ~140 cycles per MMA in the compiler's waterfall loop).
 //
-// Warp roles (256 threads, 1 CTA per SM, persistent over units):
+// Warp roles (384 threads, 1 CTA per SM, persistent over units):
 //   warp 0 lane 0 : weight producer (TMA)          warp 3 lane 0 : activation producer (TMA)
 //   warp 1        : tcgen05.mma issuer             warp 2        : TMEM allocator
-//   warps 4..7    : epilogue.  A thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
+//   warps 4..11   : epilogue (two warps per TMEM lane quarter, alternating 32-position chunks).  A thread owns one output CHANNEL (TMEM lane) and reads 32 positions at a time.
 //       conv : 2^-S scale + bias + LeakyReLU, then the planes the consumer needs (conv2 -> hi16, lo8, hi8 for
 //              conv3; conv3 -> hi16, lo16 for w_v / gather) stored straight to global memory: for a fixed position
 //              a warp's 32 lanes are 32 consecutive channels = one contiguous 64-byte (fp8: 32-byte) piece of the row
@@ -76,7 +76,7 @@ constexpr int kA2Region    = 2 * kARegion;                       // 272-row slab
 constexpr int kNumRegions  = 4;
 constexpr int kA2Bytes     = kNumRegions * kA2Region;            //                                        = 139264
 constexpr int kBStage      = 128 * 128;                          // one weight stage: 128 rows x 128 B     = 16384
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;                                // 4 control warps + 8 epilogue warps
 constexpr int kConvStages  = 24;                                 // conv: (region, tap)
 constexpr int kWvStages    = 4;                                  // w_v : (K-half, weight hi/lo)
 constexpr int kTWStages    = 5;                                  // weight ring depth (16 KB each)
@@ -127,7 +127,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
     tma_prefetch_desc(&tm_w);
     for (int i = 0; i < kNumRegions; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kTWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -243,7 +243,10 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
-    const int wq = warp - 4;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
+    // 8 epilogue warps: warp w may touch TMEM lanes 32*(w%4)..+31 (= 32 output channels); the two warps that share a
+    // lane quarter split the unit's eight 32-position chunks between them (even / odd).
+    const int wq = warp & 3;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
+    const int grp = (warp - 4) >> 2;                           // 0: chunks 0,2,4,6   1: chunks 1,3,5,7
     const int ch = wq * 32 + lane;
     const float bias = kWvMode ? 0.f : p.bias[ch];
     const float oscale = p.out_scale;
@@ -261,7 +264,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
+      for (int c32 = grp; c32 < 8; c32 += 2) {
         const int p0 = t0 + c32 * 32;                          // first position of this chunk
         if (p0 >= kTok) break;                                 // uniform: the rest of the unit is past the window end
         uint32_t r[32];
@@ -329,7 +332,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
-    if (p.dbg && warp == 4 && lane == 0) {
+    if (p.dbg && warp == 4 && lane == 0) {   // (group 0's view)
       long long* d = p.dbg + blockIdx.x * 8;
       d[5] = clock64() - t_begin; d[6] = w_full_c;
     }
