@@ -245,3 +245,31 @@ def test_conv_operand_scaling_rule(shipped):
         c.close()
     assert np.abs(p - ref).max() <= TOL
     assert np.array_equal(p.argmax(1), ref.argmax(1))
+
+
+def test_module_mixed_lengths_single_window_and_n_rich(tmp_path, shipped):
+    """BASELINE config 5 shape in miniature: contig lengths 1 kb - 60 kb, lower-case and N-rich stretches, a contig that is
+    dropped after stripping, CRLF line ends; multi-window and --single-window runs against the oracle pipeline."""
+    from genomad_b200 import nn_classification, _paths
+    rng = np.random.default_rng(12)
+    recs = []
+    for i, ln in enumerate([1000, 2499, 2500, 6000, 6001, 8500, 14499, 33000, 60000, 12000]):
+        s = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.choice(9, ln, p=[.22, .22, .22, .22, .025, .025, .025, .025, .02])].copy()
+        if i == 7:
+            s[6000:11000] = ord("N")          # window 1 has > 4000 N -> skipped by the reference's rule
+        if i == 9:
+            s[:700] = ord("N"); s[-900:] = ord("n")   # stripped before windowing
+        recs.append(f">ctg{i} len={ln}\r\n" + "\r\n".join(s.tobytes().decode()[k:k + 70] for k in range(0, ln, 70)))
+    recs.append(">all_n\r\nNNNNNNNNNNnnnnnnnn")
+    fa = tmp_path / "mixed.fna"
+    fa.write_text("\r\n".join(recs) + "\r\n", newline="")
+    for single in (False, True):
+        out = tmp_path / f"out{int(single)}"
+        nn_classification.main(fa, out, single, 16, False, 2, False, True)
+        z = np.load(_paths.NNOutputs("mixed", out).nn_classification_npz_output)
+        names, ids, ascii_arr, tok = T.encode_fasta(fa, single_window=single)
+        ref = T.segment_mean(_oracle_probs(tok, shipped), ids, len(names))
+        assert list(z["contig_names"]) == list(names) and "all_n" not in list(names)
+        assert np.abs(z["predictions"] - ref).max() <= TOL
+        assert np.array_equal(z["predictions"].argmax(1), ref.argmax(1))
+        assert not _paths.NNOutputs("mixed", out).encoded_sequences_dir.exists()      # --cleanup
