@@ -49,6 +49,7 @@ struct gnm_fasta {
   std::vector<int64_t> kept;       // indices of records whose stripped sequence is non-empty
   std::unique_ptr<uint8_t[]> comp; // compacted sequences (uninitialised), record i inside its own raw body span
   std::vector<std::vector<int32_t>> win_start;   // per kept record: start (in nt) of each kept window
+  std::vector<int32_t> flat_rec, flat_start;     // per window (global order): kept-record index, start in nt
   int64_t n_windows = 0;
   int64_t n_nonempty_raw = 0;      // records with a non-empty sequence before stripping (what check_fasta counts)
   int has_dup = 0;
@@ -149,6 +150,7 @@ extern "C" int gnm_fasta_parse(const uint8_t* text, size_t len_, int single_wind
     if (R.seq_len > 0) {
       R.first_window = f->n_windows;
       f->n_windows += R.n_windows;
+      for (int32_t st : wins[r]) { f->flat_rec.push_back(static_cast<int32_t>(f->kept.size())); f->flat_start.push_back(st); }
       f->kept.push_back(static_cast<int64_t>(r));
       f->win_start.push_back(std::move(wins[r]));
     }
@@ -206,6 +208,29 @@ extern "C" int gnm_fasta_export(const gnm_fasta* f, uint8_t* windows, int32_t* o
       }
     });
   }
+  return 0;
+}
+
+// windows [first, first + count) of the global window list -> dst [count][6000]  (streaming export: the driver fills one
+// pinned chunk while the GPU classifies the previous one)
+extern "C" int gnm_fasta_export_windows(const gnm_fasta* f, int64_t first, int64_t count, uint8_t* dst, int threads) {
+  if (!f || !dst) { g_fasta_err = "gnm_fasta_export_windows: null argument"; return 1; }
+  if (first < 0 || count < 0 || first + count > f->n_windows) { g_fasta_err = "gnm_fasta_export_windows: range out of bounds"; return 1; }
+  constexpr int64_t kBlock = 64;                            // windows per work item
+  parallel_for((count + kBlock - 1) / kBlock, threads, [&](int64_t b) {
+    const int64_t lo = first + b * kBlock, hi = std::min(first + count, lo + kBlock);
+    for (int64_t wdx = lo; wdx < hi; ++wdx) {
+      const Record& R = f->recs[f->kept[f->flat_rec[wdx]]];
+      const uint8_t* s = f->comp.get() + R.seq_off;
+      uint8_t* out = dst + (wdx - first) * kWin;
+      const int64_t st = f->flat_start[wdx], n = std::min<int64_t>(kWin, R.seq_len - st);
+      for (int64_t j = 0; j < n; ++j) {
+        const uint8_t c = s[st + j];
+        out[j] = (c >= 'a' && c <= 'z') ? static_cast<uint8_t>(c - 32) : c;
+      }
+      if (n < kWin) std::memset(out + n, 'N', static_cast<size_t>(kWin - n));
+    }
+  });
   return 0;
 }
 

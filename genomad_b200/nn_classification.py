@@ -4,10 +4,11 @@
 (<prefix>_nn_classification.{log,json,tsv,npz}, <prefix>_encoded_sequences/, the provirus twins), same
 skip/restart/cleanup semantics, same error behaviour (message + sys.exit(1)).
 
-What changed underneath: the FASTA is turned into one dense uint8 window matrix on the host
-(genomad_b200.sequence), shipped to the B200 in steps of ``batch_size`` windows, tokenised and
-classified by libgnm.so (hand-written sm_100a kernels), and reduced per contig on the device.
-TensorFlow, TFRecords and the per-batch ``predict`` call are gone.  With torchrun (WORLD_SIZE > 1)
+What changed underneath: the FASTA is parsed once by the native reader (csrc/fasta.cpp); its 6 kb windows
+are streamed through pinned chunks to the B200 (the host fills chunk i+1 while the GPU classifies chunk i),
+tokenised and classified by libgnm.so (hand-written sm_100a kernels) in steps of ``batch_size`` windows, and
+reduced per contig on the device.  TensorFlow, TFRecords and the per-batch ``predict`` call are gone; the
+"encoded sequences" directory only records which window belongs to which sequence.  With torchrun (WORLD_SIZE > 1)
 windows are sharded across GPUs and combined over NCCL (genomad_b200.dist); rank 0 writes the outputs.
 """
 from __future__ import annotations
@@ -30,36 +31,62 @@ def _make_classifier(batch_size: int, device: int):
     return Classifier(None, device=device, max_batch=max(1, int(batch_size)))
 
 
-def _pinned_windows(n: int):
-    """uint8 [n, 6000] in page-locked host memory when a GPU is present (H2D copies then overlap compute)."""
-    try:
-        import torch
-        if n > 0 and torch.cuda.is_available():
-            t = torch.empty((n, sequence.WINDOW), dtype=torch.uint8).pin_memory()
-            arr = t.numpy()
-            _PINNED_KEEPALIVE.append(t)
-            return arr
-    except Exception:
-        pass
-    return None
-
-
-_PINNED_KEEPALIVE: list = []
-
-
-def _classify_windows(clf, windows: np.ndarray, offsets: np.ndarray, info: gdist.DistInfo,
-                      contig_reduce: str = "gather") -> np.ndarray:
-    """windows uint8 [W,6000] + contig offsets -> float32 [n_contigs,3] per-contig mean (identical on all ranks)."""
+def _pinned_chunk(n: int):
+    """uint8 [n, 6000] in page-locked host memory (H2D copies then run at full PCIe speed and overlap compute)."""
     import torch
-    n = windows.shape[0]
+    t = torch.empty((n, sequence.WINDOW), dtype=torch.uint8).pin_memory()
+    return t, t.numpy()
+
+
+def _classify_parsed(clf, parsed, offsets: np.ndarray, info: gdist.DistInfo, contig_reduce: str = "gather") -> np.ndarray:
+    """
+    Parsed FASTA -> float32 [n_contigs, 3] per-contig mean (identical on all ranks).
+
+    This rank's contiguous block of the global window list is streamed in chunks: the native reader fills one pinned
+    chunk (upper-case + pad, multi-threaded) while the GPU classifies the previous one (gnm_classify_host on a worker
+    thread; the C call releases the GIL).  Windows never exist on disk.
+    """
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    n = parsed.n_windows
     start, end = gdist.shard_bounds(n, info.world_size, info.rank)
-    local = clf.classify_host(windows[start:end])                              # [W_local, 3] float32 (host)
+    chunk = max(4 * clf.max_batch, 4096)
+    keep, bufs = zip(*(_pinned_chunk(min(chunk, max(1, end - start))) for _ in range(2)))
+    parts, futures = [], []
+    with ThreadPoolExecutor(max_workers=1) as gpu:
+        for i, a in enumerate(range(start, end, chunk)):
+            b = min(end, a + chunk)
+            if i >= 2:
+                parts.append(futures[i - 2].result())            # buffer i%2 is free again
+            win = parsed.export_windows(a, b - a, bufs[i % 2])
+            futures.append(gpu.submit(clf.classify_host, win))
+        for f in futures[len(parts):]:
+            parts.append(f.result())
+    local = np.concatenate(parts) if parts else np.zeros((0, 3), np.float32)
+    del keep
     dev = torch.device("cuda", clf.device)
     local_t = torch.from_numpy(local).to(dev)
     if contig_reduce == "allreduce" and info.world_size > 1:
         loc_off = torch.from_numpy(gdist.local_offsets(offsets, start, end)).to(dev)
-        partials = clf.segment_sum(local_t, loc_off)
-        partials = gdist.allreduce_partials(partials, info.world_size)
+        partials = gdist.allreduce_partials(clf.segment_sum(local_t, loc_off), info.world_size)
+        return gdist.finish_mean(partials).cpu().numpy()
+    probs = gdist.gather_window_probs(local_t, n, info.world_size)
+    off_t = torch.from_numpy(offsets.astype(np.int32)).to(dev)
+    return clf.segment_mean(probs, off_t).cpu().numpy()
+
+
+def _classify_windows(clf, windows: np.ndarray, offsets: np.ndarray, info: gdist.DistInfo,
+                      contig_reduce: str = "gather") -> np.ndarray:
+    """Same reduction for a window matrix that is already in memory (tools/multigpu_check.py, tests)."""
+    import torch
+    n = windows.shape[0]
+    start, end = gdist.shard_bounds(n, info.world_size, info.rank)
+    local = clf.classify_host(windows[start:end])
+    dev = torch.device("cuda", clf.device)
+    local_t = torch.from_numpy(local).to(dev)
+    if contig_reduce == "allreduce" and info.world_size > 1:
+        loc_off = torch.from_numpy(gdist.local_offsets(offsets, start, end)).to(dev)
+        partials = gdist.allreduce_partials(clf.segment_sum(local_t, loc_off), info.world_size)
         return gdist.finish_mean(partials).cpu().numpy()
     probs = gdist.gather_window_probs(local_t, n, info.world_size)
     off_t = torch.from_numpy(offsets.astype(np.int32)).to(dev)
@@ -73,38 +100,26 @@ def _write_tsv(path: Path, names, preds) -> None:
             fout.write(f"{name}\t{float(s[0]):.4f}\t{float(s[1]):.4f}\t{float(s[2]):.4f}\n")
 
 
-def _encode_stage(console, fasta_path, enc_dir: Path, id_path: Path, single_window, names_key, ids_key, what, is_main,
-                  parsed=None, keep_windows=True):
+def _encode_stage(console, enc_dir: Path, id_path: Path, names_key, ids_key, what, is_main, parsed):
+    """
+    The reference's "encoding" stage (nn_classification.py:215-246) wrote TFRecords of tokens; here tokens never exist on
+    the host, so the stage only records which window belongs to which sequence (<prefix>_seq_window_id.npz, same keys).
+    """
     if enc_dir.is_dir() and is_main:
         shutil.rmtree(enc_dir)
     console.log(f"Creating the {enc_dir} directory.")
     if is_main:
         enc_dir.mkdir()
-    if parsed is None:
-        parsed = sequence.ParsedFasta(fasta_path, single_window)
-    enc = parsed.encode(_pinned_windows(parsed.n_windows))      # written straight into page-locked memory
-    parsed.close()
+    index = parsed.index()
     if is_main:
-        np.savez_compressed(id_path, **{names_key: enc.names, ids_key: enc.contig_ids})
-        if keep_windows:                  # with --cleanup the directory is deleted right after classification
-            np.save(enc_dir / f"{len(enc.contig_ids)}.windows.npy", enc.windows)
+        np.savez_compressed(id_path, **{names_key: index.names, ids_key: index.contig_ids})
     console.log(f"Encoded {what} data written to {enc_dir.name}.")
-    return enc
-
-
-def _load_encoded(enc_dir: Path, id_path: Path, names_key, ids_key):
-    z = np.load(id_path)
-    names, ids = z[names_key], z[ids_key]
-    files = sorted(enc_dir.glob("*.windows.npy"))
-    windows = np.load(files[0])
-    counts = np.bincount(ids, minlength=len(names)) if len(ids) else np.zeros(len(names), np.int64)
-    offsets = np.zeros(len(names) + 1, np.int32)
-    np.cumsum(counts, out=offsets[1:])
-    return sequence.EncodedFasta(names, ids, offsets, windows)
+    return index
 
 
 def main(input_path, output_path, single_window, batch_size, restart, threads, verbose, cleanup):
     input_path, output_path = Path(input_path), Path(output_path)
+    utils.start_md5(input_path)                          # hashed in the background while the file is parsed
     info = gdist.init_process_group_if_needed()
     is_main = info.is_main
     if not output_path.is_dir() and is_main:
@@ -155,13 +170,17 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
         utils.write_execution_info("nn_classification", input_path, parameter_dict,
                                    outputs.nn_classification_execution_info)
 
-    clf = None
+    # the classifier (CUDA context, weight upload, TMA descriptors: ~0.3 s) is built on a helper thread while the host
+    # parses; it is only joined when a job really has windows to classify
+    from concurrent.futures import ThreadPoolExecutor
+    clf_pool = ThreadPoolExecutor(max_workers=1)
+    clf_future = None
 
     def classifier():
-        nonlocal clf
-        if clf is None:
-            clf = _make_classifier(batch_size, info.local_rank)
-        return clf
+        nonlocal clf_future
+        if clf_future is None:
+            clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)
+        return clf_future.result()
 
     jobs = [("sequence", "contig", input_path, outputs.encoded_sequences_dir, outputs.seq_window_id_output,
              "contig_names", "contig_ids", outputs.nn_classification_npz_output, outputs.nn_classification_output, True)]
@@ -169,35 +188,41 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
         jobs.append(("provirus", "provirus", outputs.find_proviruses_nucleotide_output, outputs.encoded_proviruses_dir,
                      outputs.provirus_window_id_output, "provirus_names", "provirus_ids",
                      outputs.provirus_nn_classification_npz_output, outputs.provirus_nn_classification_output, False))
+    if not (skip and all(j[7].exists() for j in jobs)):
+        clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)      # start now, overlap with parsing
 
     for what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows in jobs:
-        # ---- encode
-        enc = None
-        if skip and id_path.exists() and len(list(enc_dir.glob("*.windows.npy"))):
+        need_classify = not (skip and npz_path.exists())
+        parsed = index = None
+        # ---- encode (here: record the window -> sequence map; the windows themselves are streamed to the GPU below)
+        if skip and id_path.exists():
             console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
-            if not (skip and npz_path.exists()):
-                enc = _load_encoded(enc_dir, id_path, names_key, ids_key)
         else:
-            enc = _encode_stage(console, fasta, enc_dir, id_path, single_window, names_key, ids_key, what, is_main,
-                                parsed=parsed_input if what == "sequence" else None, keep_windows=not cleanup)
+            parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window)
+            index = _encode_stage(console, enc_dir, id_path, names_key, ids_key, what, is_main, parsed)
         # ---- classify
-        if skip and npz_path.exists():
+        if not need_classify:
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")
             z = np.load(npz_path)
             names, preds = z[names_key], z["predictions"]
         else:
-            if enc.windows.shape[0] == 0:
+            if parsed is None:
+                parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window)
+                index = parsed.index()
+            if parsed.n_windows == 0:
                 if must_have_windows:
                     console.error("No sequences were found. Please check your input FASTA.")
                     sys.exit(1)
-                names, preds = enc.names, np.zeros((len(enc.names), 3), np.float32)
+                names, preds = index.names, np.zeros((len(index.names), 3), np.float32)
             else:
-                preds = _classify_windows(classifier(), enc.windows, enc.offsets, info)
-                names = enc.names
+                preds = _classify_parsed(classifier(), parsed, index.offsets, info)
+                names = index.names
             console.log(f"{'Sequences' if what == 'sequence' else 'Proviruses'} classified.")
             if is_main:
                 np.savez_compressed(npz_path, **{names_key: names, "predictions": preds.astype(np.float32)})
             console.log(f"{noun.capitalize()} classification in binary format written to {npz_path.name}.")
+        if parsed is not None:
+            parsed.close()
         if cleanup and enc_dir.is_dir() and is_main:
             console.log(f"Deleting encoded {what} data.")
             shutil.rmtree(enc_dir)
@@ -205,5 +230,5 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             _write_tsv(tsv_path, names, preds)
         console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
 
-    _PINNED_KEEPALIVE.clear()
+    clf_pool.shutdown(wait=True)
     console.log("geNomad nn-classification finished!")

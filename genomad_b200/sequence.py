@@ -210,6 +210,29 @@ class ParsedFasta:
         ids = np.repeat(np.arange(nc, dtype=np.int64), np.diff(offsets))
         return EncodedFasta(names, ids, offsets, win)
 
+    def index(self) -> EncodedFasta:
+        """Names, contig ids and offsets only (windows=None): what the driver needs before streaming the windows."""
+        import ctypes as C
+        nc = self.n_contigs
+        offsets = np.zeros(nc + 1, dtype=np.int32)
+        headers = C.create_string_buffer(max(1, self._header_bytes))
+        rc = self._lib.gnm_fasta_export(self._h, None, offsets.ctypes.data, headers, self._threads)
+        if rc != 0:
+            raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
+        lines = headers.raw[: self._header_bytes].decode("utf-8", errors="replace").split("\n")[:nc]
+        names = np.array([accession(h) for h in lines]) if nc else np.array([], dtype="<U1")
+        ids = np.repeat(np.arange(nc, dtype=np.int64), np.diff(offsets))
+        return EncodedFasta(names, ids, offsets, None)
+
+    def export_windows(self, first: int, count: int, out: np.ndarray) -> np.ndarray:
+        """Windows [first, first+count) of the global list -> out[:count] (uint8 [*, 6000], e.g. a pinned chunk)."""
+        assert out.dtype == np.uint8 and out.shape[1] == WINDOW and out.shape[0] >= count and out.flags.c_contiguous
+        if count:
+            rc = self._lib.gnm_fasta_export_windows(self._h, int(first), int(count), out.ctypes.data, self._threads)
+            if rc != 0:
+                raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
+        return out[:count]
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.gnm_fasta_free(self._h)

@@ -67,14 +67,36 @@ class HybridConsole:
 
 
 _MD5_CACHE: dict = {}
+_MD5_PENDING: dict = {}
+
+
+def _md5_key(path):
+    st = os.stat(path)
+    return (str(Path(path).resolve()), st.st_size, st.st_mtime_ns)
+
+
+def start_md5(path) -> None:
+    """Begin hashing `path` on a helper thread (hashlib releases the GIL); get_md5() joins it."""
+    import threading
+    key = _md5_key(path)
+    if key in _MD5_CACHE or key in _MD5_PENDING:
+        return
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("v", _md5_uncached(path)), daemon=True)
+    t.start()
+    _MD5_PENDING[key] = (t, box)
 
 
 def get_md5(path, size: int = 1 << 20) -> str:
     """md5 of a file; memoised on (path, size, mtime) -- the reference re-hashes the input up to three times per run."""
-    st = os.stat(path)
-    key = (str(Path(path).resolve()), st.st_size, st.st_mtime_ns)
+    key = _md5_key(path)
     if key in _MD5_CACHE:
         return _MD5_CACHE[key]
+    if key in _MD5_PENDING:
+        t, box = _MD5_PENDING.pop(key)
+        t.join()
+        _MD5_CACHE[key] = digest = box["v"]
+        return digest
     _MD5_CACHE[key] = digest = _md5_uncached(path, size)
     return digest
 

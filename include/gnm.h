@@ -142,6 +142,8 @@ int gnm_fasta_parse(const uint8_t* text, size_t len, int single_window, int thre
 int gnm_fasta_info(const gnm_fasta* f, int64_t* n_records_nonempty, int* has_duplicate_ids, int64_t* n_contigs,
                    int64_t* n_windows, int64_t* header_bytes);
 int gnm_fasta_export(const gnm_fasta* f, uint8_t* windows, int32_t* offsets, char* headers, int threads);
+/* windows [first, first + count) of the global window list -> dst uint8 [count][6000] (streaming export) */
+int gnm_fasta_export_windows(const gnm_fasta* f, int64_t first, int64_t count, uint8_t* dst, int threads);
 void gnm_fasta_free(gnm_fasta* f);
 
 /* ---- introspection / test hooks (not needed by a drop-in caller) ------------------------- */

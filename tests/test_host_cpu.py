@@ -152,10 +152,11 @@ def stub_driver(monkeypatch):
     _StubClassifier.calls = 0
     monkeypatch.setattr(nn_classification, "_make_classifier", lambda batch_size, device: _StubClassifier())
 
-    def fake_classify(clf, windows, offsets, info, contig_reduce="gather"):
+    def fake_classify(clf, parsed, offsets, info, contig_reduce="gather"):
+        windows = parsed.export_windows(0, parsed.n_windows, np.zeros((max(1, parsed.n_windows), 6000), np.uint8))
         return T.segment_mean(clf.classify_host(windows), np.repeat(np.arange(len(offsets) - 1), np.diff(offsets)),
                               len(offsets) - 1)
-    monkeypatch.setattr(nn_classification, "_classify_windows", fake_classify)
+    monkeypatch.setattr(nn_classification, "_classify_parsed", fake_classify)
     return _StubClassifier
 
 
