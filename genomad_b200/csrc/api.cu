@@ -80,9 +80,7 @@ struct gnm_handle {
   DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
   CUtensorMap tm_act[2];
   CUtensorMap tm_w[4];
-  int last_n = 0;
   StageTimer timer;
-  std::vector<float> stage_ms;
   std::vector<void*> allocs;
 };
 
@@ -462,7 +460,6 @@ static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
 // One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
 static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
                         cudaStream_t st) {
-  h->last_n = n;
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   h->ybuf_fp8lo[0] = h->ybuf_fp8lo[1] = 0;
   timer_mark(h, "embed_conv1", st);

@@ -151,7 +151,9 @@ void gnm_fasta_free(gnm_fasta* f);
 /* Options: "conv_impl" 0 = tcgen05 tensor-core path (default), 1 = fp32 CUDA-core validation
  * kernels (test hook: lets the tensor-core path be checked on the GPU at large batch);
  * "debug_stop" 0 = full pipeline, 1 = stop after layer 1 + gather#0, 2 = after conv2, 3 = after conv3;
- * "profile_stages" 1 = record a CUDA event between stages (see gnm_stage_times). */
+ * "profile_stages" 1 = record a CUDA event between stages (see gnm_stage_times);
+ * "conv_experiment" bit mask for timing experiments on the conv kernel: 2 = skip the epilogue's global stores (results
+ * become wrong), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg"). */
 int gnm_set_option(gnm_handle* h, const char* name, int value);
 int gnm_get_option(gnm_handle* h, const char* name, int* value);
 
@@ -168,7 +170,8 @@ int gnm_stage_times(gnm_handle* h, const char** names, float* ms, int* count);
  * Copy an intermediate of the most recent forward step (first n <= max_batch windows) to a device
  * buffer as fp32.  which: "buf0","buf1" = the two activation buffers [n][5997][128] (after a full
  * step buf0 = y3, buf1 = y2; with debug_stop = 1, buf0 = y1); "q0","q1" [n][749][128];
- * "mpi0","mpi1" [n][2100]; "logits" [n][752]; "h0" [n][256].  Used by the per-kernel parity tests.
+ * "mpi0","mpi1" [n][2100]; "logits" [n][752]; "h0" [n][256]; "conv_dbg" [num_sms][16] (int64 counters viewed as
+ * float pairs).  Used by the per-kernel parity tests and tools/gpu_experiment.py.
  */
 int gnm_debug_fetch(gnm_handle* h, const char* which, int n, float* d_dst, void* stream);
 
