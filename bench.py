@@ -312,8 +312,7 @@ def main():
                 for name, key, gb in (
                     ("patch_stream_kernel (IGLOO patch gather, 8400 rows x 512 B per window)", "gather1", B * 4300800 / 1e9),
                     ("conv_t_kernel<true> (w_v + max-pool: reads hi16+lo16 planes once)", "wv1", B * (5997 * 512 + 749 * 512) / 1e9),
-                    ("layer1_gather_kernel (encode + layer 1 + IGLOO#0 gather: writes four planes)", "layer1+gather0",
-                     B * (6000 + 5997 * 768) / 1e9))},
+                    ("embed_conv1_kernel (encode + layer 1: writes four planes)", "embed_conv1", B * (6000 + 5997 * 768) / 1e9))},
             "stage_ms": stage_ms,
             "model_tflops_algorithmic": B * FLOP_DENSE_TOTAL / (total_ms / K * 1e-3) / 1e12,
         }

@@ -61,7 +61,6 @@ struct gnm_handle {
   float* conv_w32[2] = {nullptr, nullptr};          // Keras layout fp32 (validation kernels)
   float* wv32[2] = {nullptr, nullptr};
   float* ent_w[2] = {nullptr, nullptr}; int32_t* ent_pos[2] = {nullptr, nullptr}; int32_t* slot_of[2] = {nullptr, nullptr};
-  int32_t* pos_slot0 = nullptr;                      // [5998] CSR over positions of IGLOO#0's position-sorted entry slots
   float* wbias[2] = {nullptr, nullptr}; float* wqk[2] = {nullptr, nullptr};
   float* d0w = nullptr; float* d0b = nullptr; float* bn0_scale = nullptr; float* bn0_shift = nullptr;
   float* d1w = nullptr; float* d1b = nullptr; float* bn1_scale = nullptr; float* bn1_shift = nullptr;
@@ -259,15 +258,6 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
     if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
     if (dev_upload(h, &h->slot_of[s], slot_of.data(), slot_of.size())) return 1;
-    if (s == 0) {                                        // first slot of every position (fused layer-1 + gather kernel)
-      std::vector<int32_t> pos_slot(kTok + 1, 0);
-      size_t slot = 0;
-      for (int t = 0; t <= kTok; ++t) {
-        while (slot < order.size() && g.patches[order[slot]] < t) ++slot;
-        pos_slot[t] = static_cast<int32_t>(slot);
-      }
-      if (dev_upload(h, &h->pos_slot0, pos_slot.data(), pos_slot.size())) return 1;
-    }
     if (dev_upload(h, &h->wbias[s], g.w_bias, kPatches)) return 1;
     if (dev_upload(h, &h->wqk[s], g.w_qk, static_cast<size_t>(kPatches) * kPooled)) return 1;
     if (dev_upload(h, &h->wv32[s], g.w_v, static_cast<size_t>(kC) * kC)) return 1;
@@ -328,8 +318,6 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (make_w_map(enc, &h->tm_w[3], h->wpack[3], kWvStages)) return 1;
 
   // ---- opt in to large dynamic shared memory
-  GNM_CUDA(cudaFuncSetAttribute(layer1_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL1Smem));
-  GNM_CUDA(cudaFuncSetAttribute(layer1_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL1Smem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
@@ -472,26 +460,16 @@ static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
 // One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
 static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
                         cudaStream_t st) {
+  dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   h->ybuf_fp8lo[0] = h->ybuf_fp8lo[1] = 0;
-  // layer 1 fused with the first IGLOO kernel's patch gather: 94 position segments x window chunks, one resident wave
-  // (4 CTAs of 256 threads and 56 KB per SM)
-  int chunks = std::max(1, std::min(n, 4 * h->num_sms / kL1Segs));
-  const int wpc = (n + chunks - 1) / chunks;
-  chunks = (n + wpc - 1) / wpc;
-  dim3 lgrid(kL1Segs, chunks);
-  timer_mark(h, "layer1+gather0", st);
+  timer_mark(h, "embed_conv1", st);
   if (d_ascii)
-    layer1_gather_kernel<true><<<lgrid, kL1Threads, kL1Smem, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias,
-                                                                  h->ent_w[0], h->pos_slot0, h->ybuf[0], h->part, kGsSlots, n, wpc);
+    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
   else
-    layer1_gather_kernel<false><<<lgrid, kL1Threads, kL1Smem, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias,
-                                                                   h->ent_w[0], h->pos_slot0, h->ybuf[0], h->part, kGsSlots, n, wpc);
-  if (check_launch(h, "layer1_gather_kernel")) return 1;
-  {
-    dim3 fgrid((kPatches + 255) / 256, n);
-    patch_finish_kernel<<<fgrid, 256, 0, st>>>(h->part, h->slot_of[0], h->wbias[0], h->mpi[0], n);
-    if (check_launch(h, "patch_finish_kernel")) return 1;
-  }
+    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
+  if (check_launch(h, "embed_conv1_kernel")) return 1;
+  timer_mark(h, "gather0", st);
+  if (launch_gather(h, 0, 0, n, st)) return 1;
   if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
   if (h->conv_impl == 0) {
     timer_mark(h, "wv0", st);

@@ -66,53 +66,63 @@ encode_tokens_kernel(const uint8_t* __restrict__ ascii, uint16_t* __restrict__ t
 }
 
 // ------------------------------------------------------------------------------------------
-// K0+K1(+K4 of IGLOO#0) fused: tokens -> layer-1 activation rows -> patch-gather partials of the FIRST IGLOO kernel.
+// K0+K1 fused: one CTA per (window, 256-position segment).  Tokens are computed into shared
+// memory (from ASCII, or copied from a token buffer), then one warp per position produces the
+// 128-channel activation row and writes its four planes (768 B, layout in common.cuh).
 //
 //   y1[t] = lrelu( (A + B) + bias ),   A = (W1[0][k0] + W1[1][k1]) + W1[2][k2],  B = (W1[3][k3] + W1[4][k4]) + W1[5][k5]
 //
-// with k_j = tok[t-5+j] and padded taps contributing exactly 0.  Tokens t-5, t-4, t-3 are the 4-mers of 6 consecutive
-// bases, so A has only 4^6 = 4096 possible values when those bases are all ACGT, and likewise B: two 2 MB "triple"
-// tables (built on the host with the same fp32 operation order, so a table hit is bit-identical to the three-row sum)
-// replace six 512-byte row reads by two.  Positions next to the window start, or touching a non-ACGT base, fall back to
-// the single-row table.  (The first version, six reads per position, was L1-bandwidth bound: l1tex 97 % busy.)
-//
-// Work split: a CTA owns a 64-position segment for a whole chunk of windows (grid = 94 segments x window chunks, one
-// resident wave), so the folded patch weights of the entries that fall into its segment (they are contiguous in the
-// position-sorted slot order, ~90 x 512 B) sit in shared memory for the lifetime of the CTA.  A warp computes one
-// activation row in registers (4 channels per lane), writes its four planes (768 B, layout in common.cuh) and, while the
-// row is still in registers, takes its dot product with every patch entry at that position -- so the first IGLOO
-// kernel's gather never re-reads y1 from HBM (2.4 GB per 1024 windows).  One writer per entry slot; patch_finish_kernel
-// adds the four slots of a patch in fixed order.
+// with k_j = tok[t-5+j] and padded taps contributing exactly 0.  Tokens t-5, t-4, t-3 are the 4-mers
+// of 6 consecutive bases, so A has only 4^6 = 4096 possible values when those bases are all ACGT, and
+// likewise B: two 2 MB "triple" tables (built on the host with the same fp32 operation order, so a
+// table hit is bit-identical to the three-row sum) replace six 512-byte row reads by two.  Positions
+// next to the window start, or touching a non-ACGT base, fall back to the single-row table.  The first
+// version (six reads per position) was L1-bandwidth bound: l1tex 97 % busy (profiles/r01_small_kernels_ncu.md).
+// Now: 0.76 ms per 1024 windows = 75 % of peak DRAM write bandwidth (4.66 GB), issue slots 83 % busy (~115 warp
+// instructions per position).  Fusing the first IGLOO kernel's patch gather into this kernel (CTA per 64-position segment,
+// folded weights in shared memory, dot products on the row while it is in registers) was built and measured: correct, but
+// 2.1 ms instead of 0.76 + 0.79 ms -- the kernel is instruction-bound (~190 warp instructions per position) and the staged
+// weights cap occupancy at 3 CTAs per SM -- so the gather stays a separate streaming kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kL1Seg = 64;                            // positions per CTA
-constexpr int kL1Segs = (kTok + kL1Seg - 1) / kL1Seg; // 94
-constexpr int kL1Threads = 256;
-constexpr int kL1Win = 4;                             // windows tokenised per block-wide barrier
-constexpr int kL1MaxEnt = 112;                        // patch entries staged in shared memory (56 KB); the rest stream from L2
+constexpr int kEmbSeg = 256;
+constexpr int kEmbThreads = 256;
 constexpr int kTriple = 4096;
-constexpr int kL1Smem = kL1MaxEnt * kC * 4;
 
 template <bool kFromAscii>
-__global__ void __launch_bounds__(kL1Threads)
-layer1_gather_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict__ tokens_in,
-                     const float* __restrict__ table,    // [6][257][128]
-                     const float* __restrict__ triple,   // [2][4096][128]: A-table, B-table
-                     const float* __restrict__ bias,     // [128]
-                     const float* __restrict__ ent_w,    // [slots][128] folded patch weights / 32, position-sorted slots
-                     const int32_t* __restrict__ pos_slot,   // [5998] first slot of each position (CSR over positions)
-                     uint8_t* __restrict__ y_out,        // [n][5997][768 B] activation rows (hi16 | lo16 | lo8 | hi8)
-                     float* __restrict__ part,           // [n][part_ld] per-entry partial dot products of IGLOO#0
-                     int part_ld, int n_windows, int windows_per_cta) {
-  extern __shared__ __align__(16) float s_wf[];             // [<= kL1MaxEnt][128]
-  __shared__ int16_t s_tok[kL1Win][kL1Seg + 8];             // token at position p0 - 5 + i, or -1 (causal pad)
-  __shared__ int s_ptr[kL1Seg + 1];                         // local entry offsets of the segment's positions
-  const int p0 = blockIdx.x * kL1Seg;
-  const int npos = min(kL1Seg, kTok - p0);
-  const int s_lo = pos_slot[p0], s_hi = pos_slot[p0 + npos];
-  for (int i = threadIdx.x; i <= kL1Seg; i += kL1Threads) s_ptr[i] = pos_slot[min(p0 + i, p0 + npos)] - s_lo;
-  const int n_stage = min(s_hi - s_lo, kL1MaxEnt);
-  for (int i = threadIdx.x; i < n_stage * (kC / 4); i += kL1Threads)
-    reinterpret_cast<float4*>(s_wf)[i] = reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(s_lo) * kC)[i];
+__global__ void __launch_bounds__(kEmbThreads)
+embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict__ tokens_in,
+                   const float* __restrict__ table,   // [6][257][128]
+                   const float* __restrict__ triple,  // [2][4096][128]: A-table, B-table
+                   const float* __restrict__ bias,    // [128]
+                   uint8_t* __restrict__ y_out,       // [n][5997][768 B] activation rows (hi16 | lo16 | lo8 | hi8)
+                   int n_windows) {
+  __shared__ int16_t s_tok[kEmbSeg + 8];    // s_tok[i] = token at position t0 - 5 + i, or -1 (causal pad)
+  __shared__ uint8_t s_b[kEmbSeg + 16];
+  const int w = blockIdx.y;
+  const int t0 = blockIdx.x * kEmbSeg;
+  if (kFromAscii) {
+    const uint8_t* src = ascii + static_cast<size_t>(w) * kWindow;
+    for (int i = threadIdx.x; i < kEmbSeg + 8 + 3; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      s_b[i] = (p >= 0 && p < kWindow) ? src[p] : uint8_t('N');
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kEmbSeg + 5; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      int16_t tk = -1;
+      if (p >= 0 && p < kTok)
+        tk = static_cast<int16_t>(kmer_token(base_code(s_b[i]), base_code(s_b[i + 1]),
+                                             base_code(s_b[i + 2]), base_code(s_b[i + 3])));
+      s_tok[i] = tk;
+    }
+  } else {
+    const uint16_t* src = tokens_in + static_cast<size_t>(w) * kTok;
+    for (int i = threadIdx.x; i < kEmbSeg + 5; i += blockDim.x) {
+      const int p = t0 - 5 + i;
+      s_tok[i] = (p >= 0 && p < kTok) ? static_cast<int16_t>(src[p]) : int16_t(-1);
+    }
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 b4 = reinterpret_cast<const float4*>(bias)[lane];
   const float4* tab4 = reinterpret_cast<const float4*>(table);
@@ -121,76 +131,45 @@ layer1_gather_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restri
     return tk >= 0 ? __ldg(tab4 + (static_cast<size_t>(j) * kVocab + tk) * (kC / 4) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   auto add4 = [](float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
-  const int w_begin = blockIdx.y * windows_per_cta;
-  const int w_end = min(n_windows, w_begin + windows_per_cta);
-
-  for (int w0 = w_begin; w0 < w_end; w0 += kL1Win) {
-    const int nw = min(kL1Win, w_end - w0);
-    __syncthreads();                                        // previous group's tokens are no longer read (also covers the staging above)
-    for (int idx = threadIdx.x; idx < nw * (kL1Seg + 5); idx += kL1Threads) {
-      const int k = idx / (kL1Seg + 5), i = idx - k * (kL1Seg + 5);
-      const int p = p0 - 5 + i;
-      int16_t tk = -1;
-      if (p >= 0 && p < kTok) {
-        if (kFromAscii) {
-          const uint8_t* src = ascii + static_cast<size_t>(w0 + k) * kWindow + p;
-          tk = static_cast<int16_t>(kmer_token(base_code(src[0]), base_code(src[1]), base_code(src[2]), base_code(src[3])));
-        } else {
-          tk = static_cast<int16_t>(tokens_in[static_cast<size_t>(w0 + k) * kTok + p]);
-        }
-      }
-      s_tok[k][i] = tk;
-    }
-    __syncthreads();
-    for (int item = warp; item < nw * npos; item += kL1Threads / 32) {
-      const int k = item / npos, i = item - k * npos;
-      const int w = w0 + k, t = p0 + i;
-      int tk[kTaps];
+  for (int i = warp; i < kEmbSeg; i += kEmbThreads / 32) {
+    const int t = t0 + i;
+    if (t >= kTok) break;
+    int tk[kTaps];
 #pragma unroll
-      for (int j = 0; j < kTaps; ++j) tk[j] = s_tok[k][i + j];        // token at position t - 5 + j
-      float4 A, B;
-      if (tk[0] > 0 && tk[2] > 0) {                                   // bases t-5 .. t all ACGT (implies tk[1] > 0)
-        const int code = ((tk[0] - 1) << 4) | ((tk[2] - 1) & 15);
-        A = __ldg(tri4 + static_cast<size_t>(code) * (kC / 4) + lane);
-      } else {
-        A = add4(add4(row(0, tk[0]), row(1, tk[1])), row(2, tk[2]));
-      }
-      if (tk[3] > 0 && tk[5] > 0) {                                   // bases t-2 .. t+3 all ACGT (implies tk[4] > 0)
-        const int code = ((tk[3] - 1) << 4) | ((tk[5] - 1) & 15);
-        B = __ldg(tri4 + (static_cast<size_t>(kTriple) + code) * (kC / 4) + lane);
-      } else {
-        B = add4(add4(row(3, tk[3]), row(4, tk[4])), row(5, tk[5]));
-      }
-      float4 a = add4(A, B);
-      // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
-      a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
-      a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
-      __half2 h01, h23, l01, l23;
-      split2_f16(a.x, a.y, h01, l01);
-      split2_f16(a.z, a.w, h23, l23);
-      const float2 fa = __half22float2(h01), fb = __half22float2(h23);
-      uint8_t* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
-      *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) =
-          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-      *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) =
-          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-      *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
-          static_cast<uint32_t>(pack_e4m3x2((a.x - fa.x) * kLo8Scale, (a.y - fa.y) * kLo8Scale)) |
-          (static_cast<uint32_t>(pack_e4m3x2((a.z - fb.x) * kLo8Scale, (a.w - fb.y) * kLo8Scale)) << 16);
-      *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
-          static_cast<uint32_t>(pack_e4m3x2(fa.x * kHi8Scale, fa.y * kHi8Scale)) |
-          (static_cast<uint32_t>(pack_e4m3x2(fb.x * kHi8Scale, fb.y * kHi8Scale)) << 16);
-      // patch entries at this position: dot(Y, Wf/32) = dot(y1, Wf), the row still being in registers
-      for (int e = s_ptr[i]; e < s_ptr[i + 1]; ++e) {
-        const float4 wv = e < kL1MaxEnt ? *reinterpret_cast<const float4*>(s_wf + e * kC + lane * 4)
-                                        : __ldg(reinterpret_cast<const float4*>(ent_w + static_cast<size_t>(s_lo + e) * kC) + lane);
-        float acc = a.x * wv.x;
-        acc = fmaf(a.y, wv.y, acc); acc = fmaf(a.z, wv.z, acc); acc = fmaf(a.w, wv.w, acc);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) part[static_cast<size_t>(w) * part_ld + s_lo + e] = acc;
-      }
+    for (int j = 0; j < kTaps; ++j) tk[j] = s_tok[i + j];          // token at position t - 5 + j
+    float4 A, B;
+    if (tk[0] > 0 && tk[2] > 0) {                                   // bases t-5 .. t all ACGT (implies tk[1] > 0)
+      const int code = ((tk[0] - 1) << 4) | ((tk[2] - 1) & 15);
+      A = __ldg(tri4 + static_cast<size_t>(code) * (kC / 4) + lane);
+    } else {
+      A = add4(add4(row(0, tk[0]), row(1, tk[1])), row(2, tk[2]));
     }
+    if (tk[3] > 0 && tk[5] > 0) {                                   // bases t-2 .. t+3 all ACGT (implies tk[4] > 0)
+      const int code = ((tk[3] - 1) << 4) | ((tk[5] - 1) & 15);
+      B = __ldg(tri4 + (static_cast<size_t>(kTriple) + code) * (kC / 4) + lane);
+    } else {
+      B = add4(add4(row(3, tk[3]), row(4, tk[4])), row(5, tk[5]));
+    }
+    float4 a = add4(A, B);
+    // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
+    a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
+    a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
+    __half2 h01, h23, l01, l23;
+    split2_f16(a.x, a.y, h01, l01);
+    split2_f16(a.z, a.w, h23, l23);
+    const float2 fa = __half22float2(h01), fb = __half22float2(h23);
+    const float f0 = fa.x, f1 = fa.y, f2 = fb.x, f3 = fb.y;
+    uint8_t* rowp = y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
+    *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
+        static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, (a.y - f1) * kLo8Scale)) |
+        (static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, (a.w - f3) * kLo8Scale)) << 16);
+    *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
+        static_cast<uint32_t>(pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale)) |
+        (static_cast<uint32_t>(pack_e4m3x2(f2 * kHi8Scale, f3 * kHi8Scale)) << 16);
   }
 }
 
