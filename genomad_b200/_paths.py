@@ -85,3 +85,71 @@ class NNOutputs:
     @property
     def find_proviruses_genes_output(self) -> Path:
         return self.find_proviruses_dir / f"{self.prefix}_provirus_genes.tsv"
+
+
+@dataclass(frozen=True)
+class AggregatedOutputs(NNOutputs):
+    """
+    What aggregated-classification reads (marker-classification's NPZ files, reference _paths.py:129-181) and writes
+    (reference _paths.py:238-281), on top of the nn-classification files above.
+    """
+
+    def _mk(self, name: str) -> Path:
+        return self.marker_classification_dir / f"{self.prefix}_{name}"
+
+    def _agg(self, name: str) -> Path:
+        return self.aggregated_classification_dir / f"{self.prefix}_{name}"
+
+    # ---- produced by marker-classification, only read here
+    @property
+    def marker_classification_dir(self) -> Path:
+        return self.output_dir / f"{self.prefix}_marker_classification"
+
+    @property
+    def marker_classification_execution_info(self) -> Path:
+        return self._mk("marker_classification.json")
+
+    @property
+    def features_npz_output(self) -> Path:
+        return self._mk("features.npz")
+
+    @property
+    def marker_classification_npz_output(self) -> Path:
+        return self._mk("marker_classification.npz")
+
+    @property
+    def provirus_features_npz_output(self) -> Path:
+        return self._mk("provirus_features.npz")
+
+    @property
+    def provirus_marker_classification_npz_output(self) -> Path:
+        return self._mk("provirus_marker_classification.npz")
+
+    # ---- written by aggregated-classification
+    @property
+    def aggregated_classification_log(self) -> Path:
+        return self.output_dir / f"{self.prefix}_aggregated_classification.log"
+
+    @property
+    def aggregated_classification_dir(self) -> Path:
+        return self.output_dir / f"{self.prefix}_aggregated_classification"
+
+    @property
+    def aggregated_classification_execution_info(self) -> Path:
+        return self._agg("aggregated_classification.json")
+
+    @property
+    def aggregated_classification_output(self) -> Path:
+        return self._agg("aggregated_classification.tsv")
+
+    @property
+    def aggregated_classification_npz_output(self) -> Path:
+        return self._agg("aggregated_classification.npz")
+
+    @property
+    def provirus_aggregated_classification_output(self) -> Path:
+        return self._agg("provirus_aggregated_classification.tsv")
+
+    @property
+    def provirus_aggregated_classification_npz_output(self) -> Path:
+        return self._agg("provirus_aggregated_classification.npz")

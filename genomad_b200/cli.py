@@ -1,6 +1,7 @@
 """
 Command line of the nn-classification module -- same arguments and options as
-``genomad nn-classification`` (reference genomad/cli.py:714-774).  rich-click is not a dependency;
+``genomad nn-classification`` (reference genomad/cli.py:714-774) -- and of its direct consumer
+``genomad aggregated-classification`` (reference cli.py:776-803).  rich-click is not a dependency;
 plain click gives the same option surface.
 
     python -m genomad_b200.cli nn-classification [OPTIONS] INPUT OUTPUT
@@ -44,6 +45,20 @@ def nn_classification(input, output, single_window, batch_size, restart, threads
     the results to the OUTPUT directory."""
     from . import nn_classification as module
     module.main(input, output, single_window, batch_size, restart, threads, verbose, cleanup)
+
+
+@cli.command(name="aggregated-classification", context_settings=CONTEXT_SETTINGS)
+@click.argument("input", type=click.Path(path_type=Path, exists=True))
+@click.argument("output", type=click.Path(path_type=Path))
+@click.option("--restart", is_flag=True, default=False, show_default=True,
+              help="Overwrite existing intermediate files.")
+@click.option("--verbose/--quiet", "-v/-q", is_flag=True, default=True, show_default=True,
+              help="Display the execution log.")
+def aggregated_classification(input, output, restart, verbose):
+    """Aggregate the results of the marker-classification and nn-classification modules to classify the sequences in
+    the INPUT file (FASTA format) and write the results to the OUTPUT directory (reference cli.py:776-803)."""
+    from . import aggregated_classification as module
+    module.main(input, output, restart, verbose)
 
 
 if __name__ == "__main__":
