@@ -13,7 +13,7 @@ probabilities per window, reference genomad/modules/nn_classification.py:65-73,3
   value  : windows/s with inputs already resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e    : the same metric through the host-buffer C-ABI call gnm_classify_host (pinned host buffers,
            H2D of every step's windows and D2H of its probabilities inside the timed region)
-  roofline : the dominant kernel (tcgen05 Conv1D, conv2t_kernel) against the measured bf16 tensor peak
+  roofline : the dominant kernel (tcgen05 Conv1D, conv_t_kernel<false>) against the measured bf16 tensor peak
   cpu_baseline : the oracle's op-for-op restatement of the Keras graph timed on this box's host cores
 
 --impl reference times that CPU restatement (the reference's own implementation is TensorFlow, which cannot
@@ -277,7 +277,7 @@ def main():
         traffic = None
         tp = ROOT / "profiles" / "ncu_traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("conv2t_dram_bytes_per_launch_batch1024")
+            traffic = json.loads(tp.read_text()).get("conv2_dram_bytes_per_launch_batch1024")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,7 +293,7 @@ def main():
                     "ms_per_step": e2e_ms / K, "api": "gnm_classify_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv2t_kernel (causal Conv1D 128->128 k=6 + LeakyReLU, layer conv2; conv3 is the same kernel)",
+            "roofline": {"bound": "tensor", "kernel": "conv_t_kernel<false> (causal Conv1D 128->128 k=6 + LeakyReLU, layer conv2; conv3 is the same kernel)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
                          "peak_source": peaks["source"], "launch_ms": dom_ms,

@@ -40,10 +40,16 @@ def cli():
               help="Use only the first window (6,000 bases) of each sequence to perform the classification.")
 @click.option("--batch-size", type=int, default=128, show_default=True,
               help="Number of data points per batch of prediction.")
-def nn_classification(input, output, single_window, batch_size, restart, threads, verbose, cleanup):
+@click.option("--write-tfrecords", is_flag=True, default=False, show_default=True,
+              help="Also write the reference's TFRecord intermediates (<count>.tfrec) to the encoded-sequences "
+                   "directory. Not an option of the reference: it always writes them; here nothing reads them.")
+def nn_classification(input, output, single_window, batch_size, restart, threads, verbose, cleanup, write_tfrecords):
     """Classify the sequences in the INPUT file (FASTA format) using the geNomad neural network and write
     the results to the OUTPUT directory."""
+    import os
     from . import nn_classification as module
+    if write_tfrecords:
+        os.environ["GENOMAD_B200_TFRECORDS"] = "1"
     module.main(input, output, single_window, batch_size, restart, threads, verbose, cleanup)
 
 

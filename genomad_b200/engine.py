@@ -73,6 +73,10 @@ EXPORTS = {
     "gnm_fasta_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "gnm_fasta_export_windows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
     "gnm_fasta_free": (None, [C.c_void_p]),
+    "gnm_tfrecord_last_error": (C.c_char_p, []),
+    "gnm_tfrecord_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
+    "gnm_tfrecord_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "gnm_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t]),
 }
 
 

@@ -13,6 +13,7 @@ windows are sharded across GPUs and combined over NCCL (genomad_b200.dist); rank
 """
 from __future__ import annotations
 
+import os
 import shutil
 import sys
 from pathlib import Path
@@ -100,10 +101,40 @@ def _write_tsv(path: Path, names, preds) -> None:
             fout.write(f"{name}\t{float(s[0]):.4f}\t{float(s[1]):.4f}\t{float(s[2]):.4f}\n")
 
 
-def _encode_stage(console, enc_dir: Path, id_path: Path, names_key, ids_key, what, is_main, parsed):
+def tfrecords_enabled() -> bool:
+    """Opt-in (``--write-tfrecords`` / GENOMAD_B200_TFRECORDS=1): also leave the reference's ``<count>.tfrec`` files."""
+    return os.environ.get("GENOMAD_B200_TFRECORDS", "0") not in ("", "0")
+
+
+def _write_tfrecords(clf, parsed, enc_dir: Path) -> int:
+    """
+    Byte-compatible stand-in for the reference's generate_data/write_tfrecord (nn_classification.py:43-82): windows are
+    tokenised on the GPU (gnm_encode), copied back as uint16 and serialised natively, 10,000 windows per file named by the
+    cumulative window count.  Returns the number of files.
+    """
+    import torch
+    from . import tfrecord
+    n, per = parsed.n_windows, tfrecord.RECORDS_PER_FILE
+    if n == 0:
+        return 0
+    keep, buf = _pinned_chunk(min(per, n))
+    dev = torch.device("cuda", clf.device)
+    files = 0
+    for a in range(0, n, per):
+        b = min(n, a + per)
+        win = parsed.export_windows(a, b - a, buf)
+        tokens = clf.encode(keep[: b - a].to(dev, non_blocking=True)).cpu().numpy()
+        assert win.shape[0] == tokens.shape[0]
+        tfrecord.write_tfrecord(enc_dir / f"{b}.tfrec", tokens)
+        files += 1
+    return files
+
+
+def _encode_stage(console, enc_dir: Path, id_path: Path, names_key, ids_key, what, is_main, parsed, classifier=None):
     """
     The reference's "encoding" stage (nn_classification.py:215-246) wrote TFRecords of tokens; here tokens never exist on
-    the host, so the stage only records which window belongs to which sequence (<prefix>_seq_window_id.npz, same keys).
+    the host, so by default the stage only records which window belongs to which sequence (<prefix>_seq_window_id.npz,
+    same keys).  With tfrecords_enabled() it also writes the reference's .tfrec files (rank 0 only).
     """
     if enc_dir.is_dir() and is_main:
         shutil.rmtree(enc_dir)
@@ -113,6 +144,9 @@ def _encode_stage(console, enc_dir: Path, id_path: Path, names_key, ids_key, wha
     index = parsed.index()
     if is_main:
         np.savez_compressed(id_path, **{names_key: index.names, ids_key: index.contig_ids})
+        if tfrecords_enabled() and classifier is not None and parsed.n_windows:
+            n_files = _write_tfrecords(classifier(), parsed, enc_dir)
+            console.log(f"{n_files} TFRecord file(s) of tokenised windows written to {enc_dir.name}.")
     console.log(f"Encoded {what} data written to {enc_dir.name}.")
     return index
 
@@ -199,7 +233,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
         else:
             parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window)
-            index = _encode_stage(console, enc_dir, id_path, names_key, ids_key, what, is_main, parsed)
+            index = _encode_stage(console, enc_dir, id_path, names_key, ids_key, what, is_main, parsed, classifier)
         # ---- classify
         if not need_classify:
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")

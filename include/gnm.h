@@ -146,6 +146,24 @@ int gnm_fasta_export(const gnm_fasta* f, uint8_t* windows, int32_t* offsets, cha
 int gnm_fasta_export_windows(const gnm_fasta* f, int64_t first, int64_t count, uint8_t* dst, int threads);
 void gnm_fasta_free(gnm_fasta* f);
 
+/* ---- TFRecord files of tokenised windows (host side, no GPU involved; off by default) ------ */
+
+/*
+ * Byte-compatible with the reference's encoding-stage intermediates: one tf.train.Example per window with
+ * features {"sequence": Int64List(5997 tokens)} in TFRecord framing -- what write_tfrecord produces
+ * (nn_classification.py:43-52) and parse_tfrecord reads (:87-91).  Nothing downstream reads these files
+ * (SURVEY.md §8f rank 4); they exist for directory-level compatibility with the reference.
+ *   gnm_tfrecord_write : tokens uint16 [n][5997] (host) -> one .tfrec file at `path` (overwritten); records are
+ *                        serialised on `threads` threads and written in window order.
+ *   gnm_tfrecord_read  : verifies both masked CRC-32C of every record; tokens may be NULL to only count records;
+ *                        fails if a record is not exactly that Example layout or if there are more than `capacity`.
+ *   gnm_crc32c         : CRC-32C (Castagnoli) of a buffer -- exposed for the known-answer tests.
+ */
+const char* gnm_tfrecord_last_error(void);
+int gnm_tfrecord_write(const char* path, const uint16_t* tokens, int64_t n, int threads);
+int gnm_tfrecord_read(const char* path, uint16_t* tokens, int64_t capacity, int64_t* n_records);
+uint32_t gnm_crc32c(const void* data, size_t n);
+
 /* ---- introspection / test hooks (not needed by a drop-in caller) ------------------------- */
 
 /* Options: "conv_impl" 0 = tcgen05 tensor-core path (default), 1 = fp32 CUDA-core validation

@@ -273,3 +273,45 @@ def test_module_mixed_lengths_single_window_and_n_rich(tmp_path, shipped):
         assert np.abs(z["predictions"] - ref).max() <= TOL
         assert np.array_equal(z["predictions"].argmax(1), ref.argmax(1))
         assert not _paths.NNOutputs("mixed", out).encoded_sequences_dir.exists()      # --cleanup
+
+
+@pytest.mark.gpu
+def test_module_tfrecord_intermediates_and_aggregation(tmp_path, shipped, monkeypatch):
+    """SURVEY §8f ranks 3-4 end to end on the GPU: with GENOMAD_B200_TFRECORDS=1 the encoded directory holds the
+    reference's <cumulative count>.tfrec files (tokens bit-exact vs the oracle tokenizer, classifying them through
+    gnm_forward_tokens reproduces the module's NPZ), and aggregated-classification consumes the module's NPZ."""
+    import torch
+    from genomad_b200 import nn_classification, aggregated_classification as agg, tfrecord, _paths, utils
+    from genomad_b200.engine import Classifier
+    monkeypatch.setenv("GENOMAD_B200_TFRECORDS", "1")
+    monkeypatch.setattr(tfrecord, "RECORDS_PER_FILE", 7)          # several files from a small input
+    rng = np.random.default_rng(3)
+    lens = [30000, 9000, 2000, 48000]
+    fa = tmp_path / "toy.fna"
+    with open(fa, "w") as f:
+        for i, ln in enumerate(lens):
+            f.write(f">c{i}\n" + np.frombuffer(b"ACGTN", np.uint8)[rng.choice(5, ln, p=[.245, .245, .245, .245, .02])].tobytes().decode() + "\n")
+    out = tmp_path / "out"
+    nn_classification.main(fa, out, False, 8, False, 2, False, False)
+    o = _paths.AggregatedOutputs("toy", out)
+    names, ids, ascii_arr, tok = T.encode_fasta(fa)
+    files = tfrecord.tfrecord_files(o.encoded_sequences_dir)
+    n = len(tok)
+    assert [int(p.stem) for p in files] == list(range(7, n, 7)) + [n]
+    back = np.concatenate([tfrecord.read_tfrecord(p) for p in files])
+    assert np.array_equal(back, tok.astype(np.uint16))
+    clf = Classifier(max_batch=8)
+    probs = clf.predict_tokens(torch.from_numpy(back).cuda()).cpu().numpy()
+    z = np.load(o.nn_classification_npz_output)
+    assert np.abs(T.segment_mean(probs, ids, len(names)) - z["predictions"]).max() <= 1e-6
+    # downstream consumer: synthetic marker branch + this run's NPZ
+    o.marker_classification_dir.mkdir()
+    utils.write_execution_info("marker_classification", fa, {}, o.marker_classification_execution_info)
+    feats = rng.random((len(names), 25)).astype(np.float32)
+    mk = rng.random((len(names), 3)).astype(np.float32)
+    np.savez_compressed(o.features_npz_output, contig_names=names, contig_features=feats)
+    np.savez_compressed(o.marker_classification_npz_output, contig_names=names, predictions=mk)
+    agg.main(fa, out, False, False)
+    a = np.load(o.aggregated_classification_npz_output)
+    assert list(a["contig_names"]) == list(names)
+    assert np.array_equal(a["predictions"], agg.branch_attention(feats[:, 15:18].sum(1), mk, z["predictions"]))
