@@ -10,6 +10,7 @@ There is no CPU or PyTorch fallback: if the library or a B200 is missing, constr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
 
@@ -18,7 +19,7 @@ import numpy as np
 from . import weights as _weights
 
 _PKG = Path(__file__).resolve().parent
-_LIB_PATH = _PKG / "libgnm.so"
+_LIB_PATH = Path(os.environ["GENOMAD_B200_LIB"]) if os.environ.get("GENOMAD_B200_LIB") else _PKG / "libgnm.so"   # dev: A/B two builds
 _lib = None
 
 WINDOW = 6000
