@@ -70,7 +70,7 @@ struct gnm_handle {
   int ybuf_fp8lo[2] = {0, 0};                        // 1 = the buffer was written by conv2 (hi16 + lo8 + hi8 only)
   float* q[2] = {nullptr, nullptr};
   float* mpi[2] = {nullptr, nullptr};
-  float* part = nullptr;                             // [max_batch][8880] per-entry partial dot products
+  float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products
   float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
@@ -242,7 +242,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   for (int s = 0; s < 2; ++s) {
     const gnm_igloo_weights& g = w->igloo[s];
     // fold the patch weights, then sort the 8400 (patch, slot) entries by position and deal them to the
-    // 8880 entry slots of patch_stream_kernel (padding slots: position 0, zero weights)
+    // kGsSlots entry slots of patch_stream_kernel (padding slots: position 0, zero weights)
     std::vector<int> order(static_cast<size_t>(kPatches) * kPatchLen);
     for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g.patches[a] < g.patches[b]; });

@@ -19,32 +19,38 @@ namespace gnm {
 // row per entry moves every popular row ~1.9x through L2 -> SM; the first version (one CTA per 32-patch
 // group, random rows) was bound by exactly that (5 TB/s L2->SM for 2.4 GB of DRAM reads,
 // profiles/r01_small_kernels_ncu.md).  Here the entries are sorted by position on the host and dealt to
-// 444 CTAs x 4 warps x 5 entries (= 3 CTAs per SM, one resident wave, no shared memory): a warp's rows
-// are neighbours in memory, repeats of a row are served by L1, and the whole grid sweeps each window
-// front to back.  Every lane keeps its 5 x 8 folded weights in registers and a 4-window deep ring of
+// 700 CTAs x 4 warps x 3 entries (= 8400 exactly; 5 CTAs per SM, one resident wave, no shared memory): a warp's
+// rows are neighbours in memory, repeats of a row are served by L1, and the whole grid sweeps each window
+// front to back.  Every lane keeps its 3 x 8 folded weights in registers and a 3-window deep ring of
 // row fragments in flight (one 512-byte row = ONE 16-byte load per lane: lanes 0-15 the fp16 "hi"
 // half-row, lanes 16-31 the "lo" half-row; lanes l and l+16 use the same weights, so hi*w and lo*w meet
-// in the warp-shuffle reduction).  Each entry has exactly one writer (part[w][slot]); patch_finish_kernel
-// then adds the four slots of a patch in fixed order k = 0..3 plus the bias, so results are deterministic.
-// Measured (profiles/r01_small_kernels_ncu.md): 0.74 ms per 1024 windows = 3.2 TB/s of DRAM reads, 40 % of peak.
-// A variant that staged the rows with 512-byte cp.async.bulk copies (6 windows deep, 184 KB in flight per SM)
-// was slower (0.88 ms), i.e. the limit is not outstanding-load capacity but DRAM efficiency on 512-byte pieces
-// requested by many CTAs at once; reading each CTA's position range as one contiguous block is the next step.
+// in the warp-shuffle reduction).  Ahead of the ring, lanes 0-11 issue one prefetch.global.L2 each per window (the
+// twelve 128-byte lines of the warp's three rows, kGsPrefetch windows further on): DRAM fetches start early at no
+// register cost and the ring's loads mostly hit L2.  Each entry has exactly one writer (part[w][slot]);
+// patch_finish_kernel then adds the four slots of a patch in fixed order k = 0..3 plus the bias, so results are
+// deterministic.
+// Measured per 1024 windows (same-box A/B, profiles/r01_small_kernels_ncu.md): 0.79 ms = 3.0 TB/s with 444 CTAs x 5
+// entries x 4-deep ring and no prefetch (12 warps per SM at 152 registers: long-scoreboard bound) -> 0.56 ms with the
+// L2 prefetch (any distance 2..8; 24 thrashes L2: 0.89 ms) -> 0.51 ms = 4.6 TB/s = 0.70 of the HBM peak with 3 entries per
+// warp and a 3-deep ring (94 registers, 20 warps per SM).  Tried and slower: 512-byte cp.async.bulk row copies into
+// shared memory (0.88 ms), 2 entries per warp (0.60-0.93 ms).
 // HBM-bound: 2.4 MB of distinct activation rows per window per IGLOO kernel (algorithmic 8400 x 512 B = 4.3 MB).
 // ------------------------------------------------------------------------------------------
-constexpr int kGsGroups = 444;                                   // CTAs (3 per SM on 148 SMs)
-constexpr int kGsPerWarp = 5;                                    // entries per warp
+constexpr int kGsPerWarp = 3;                                    // entries per warp
 constexpr int kGsThreads = 128;
-constexpr int kGsPerCta = 4 * kGsPerWarp;                        // 20
-constexpr int kGsSlots = kGsGroups * kGsPerCta;                  // 8880 >= 8400 (padded with zero-weight entries)
-constexpr int kGsDepth = 4;                                      // windows in flight per warp
+constexpr int kGsPerCta = 4 * kGsPerWarp;                        // 12
+constexpr int kGsGroups = (kPatches * kPatchLen + kGsPerCta - 1) / kGsPerCta;   // 700 CTAs (5 per SM, one wave)
+constexpr int kGsSlots = kGsGroups * kGsPerCta;                  // 8400 (any remainder would be zero-weight padding)
+constexpr int kGsDepth = 3;                                      // windows in flight per warp (registers)
+constexpr int kGsPrefetch = 4;                                   // further windows requested into L2 ahead of the ring
+constexpr int kGsMinBlocks = 5;
 static_assert(kGsSlots >= kPatches * kPatchLen, "not enough entry slots");
 
-__global__ void __launch_bounds__(kGsThreads, 3)
+__global__ void __launch_bounds__(kGsThreads, kGsMinBlocks)
 patch_stream_kernel(const uint8_t* __restrict__ y,         // [n][5997][768 B]; reads the hi16 / lo16 planes (scaled by 32)
-                    const int32_t* __restrict__ ent_pos,   // [8880] position of each slot (0 for padding)
-                    const float* __restrict__ ent_w,       // [8880][128] folded weights / 32 of each slot (0 for padding)
-                    float* __restrict__ part,              // [n][8880]
+                    const int32_t* __restrict__ ent_pos,   // [kGsSlots] position of each slot (0 for padding)
+                    const float* __restrict__ ent_w,       // [kGsSlots][128] folded weights / 32 of each slot (0 for padding)
+                    float* __restrict__ part,              // [n][kGsSlots]
                     int n_windows) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
@@ -61,6 +67,12 @@ patch_stream_kernel(const uint8_t* __restrict__ y,         // [n][5997][768 B]; 
   }
   const uint8_t* ybase = y;
   constexpr size_t kWinBytes = static_cast<size_t>(kTok) * kRowBytes;
+  // L2 prefetch kGsPrefetch windows ahead of the register ring: the first 4 * kGsPerWarp lanes each own one 128-byte
+  // line of the warp's 512-byte rows.
+  const int pf_off = lane < 4 * kGsPerWarp ? ent_pos[e0 + (lane >> 2)] * kRowBytes + kOffHi16 + (lane & 3) * 128 : -1;
+  if (pf_off >= 0)
+    for (int d = kGsDepth; d < kGsDepth + kGsPrefetch && d < n_windows; ++d)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + d * kWinBytes + pf_off));
   uint4 ring[kGsDepth][kGsPerWarp];
 #pragma unroll
   for (int d = 0; d < kGsDepth; ++d)
@@ -90,12 +102,16 @@ patch_stream_kernel(const uint8_t* __restrict__ y,         // [n][5997][768 B]; 
           for (int i = 0; i < kGsPerWarp; ++i)
             ring[d][i] = __ldg(reinterpret_cast<const uint4*>(ybase + (w + kGsDepth) * kWinBytes + rowoff[i]));
         }
+        if (pf_off >= 0 && w + kGsDepth + kGsPrefetch < n_windows)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (w + kGsDepth + kGsPrefetch) * kWinBytes + pf_off));
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
           for (int i = 0; i < kGsPerWarp; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
         if (lane < kGsPerWarp) {
-          const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : lane == 3 ? acc[3] : acc[4];
+          float r = acc[0];
+#pragma unroll
+          for (int i = 1; i < kGsPerWarp; ++i) r = lane == i ? acc[i] : r;
           part[static_cast<size_t>(w) * kGsSlots + e0 + lane] = r;
         }
       }
