@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "encode.cuh"
 #include "conv_t.cuh"
+#include "layer1_wv.cuh"
 #include "conv_ref.cuh"
 #include "igloo.cuh"
 #include "dense.cuh"
@@ -52,6 +53,7 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
+  int fuse_l1 = 0;          // 1 = layer 1 and w_v#0 in one kernel (layer1_wv.cuh; bit-identical, measured slower: off); 0 = embed_conv1_kernel + conv_t_kernel<true>
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
   float* conv1_table = nullptr; float* conv1_triple = nullptr; float* conv1_bias = nullptr;
@@ -320,6 +322,8 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- opt in to large dynamic shared memory
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
+  GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
+  GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
   GNM_CUDA(cudaDeviceSynchronize());
@@ -462,18 +466,32 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
                         cudaStream_t st) {
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   h->ybuf_fp8lo[0] = h->ybuf_fp8lo[1] = 0;
+  const bool fused = h->fuse_l1 && h->conv_impl == 0;       // layer 1 + w_v#0 in one kernel
+  if (fused) {
+    timer_mark(h, "layer1_wv0", st);
+    FusedParams fp;
+    fp.ascii = d_ascii; fp.tokens = d_tok; fp.table = h->conv1_table; fp.triple = h->conv1_triple; fp.bias = h->conv1_bias;
+    fp.y_out = h->ybuf[0]; fp.q_out = h->q[0]; fp.n_units = n * kFuUnitsPerWin; fp.status = h->status;
+    const int grid = std::min(h->num_sms, fp.n_units);
+    if (d_ascii) layer1_wv_kernel<true><<<grid, kFuThreads, kFuSmem, st>>>(h->tm_w[2], fp);
+    else layer1_wv_kernel<false><<<grid, kFuThreads, kFuSmem, st>>>(h->tm_w[2], fp);
+    if (check_launch(h, "layer1_wv_kernel")) return 1;
+  } else {
   timer_mark(h, "embed_conv1", st);
   if (d_ascii)
     embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
   else
     embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
   if (check_launch(h, "embed_conv1_kernel")) return 1;
+  }
   timer_mark(h, "gather0", st);
   if (launch_gather(h, 0, 0, n, st)) return 1;
   if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
   if (h->conv_impl == 0) {
-    timer_mark(h, "wv0", st);
-    if (launch_wv_tc(h, 0, 0, n, st)) return 1;               // y1 (buf0) -> q0
+    if (!fused) {
+      timer_mark(h, "wv0", st);
+      if (launch_wv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> q0
+    }
     timer_mark(h, "conv2", st);
     if (launch_conv(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1)
     if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
@@ -621,6 +639,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   if (k == "conv_impl") { if (value != 0 && value != 1) return fail("conv_impl must be 0 or 1"); h->conv_impl = value; }
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
+  else if (k == "fuse_l1") h->fuse_l1 = value ? 1 : 0;
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;
@@ -631,6 +650,7 @@ extern "C" int gnm_get_option(gnm_handle* h, const char* name, int* value) {
   if (k == "conv_impl") *value = h->conv_impl;
   else if (k == "debug_stop") *value = h->debug_stop;
   else if (k == "profile_stages") *value = h->profile_stages;
+  else if (k == "fuse_l1") *value = h->fuse_l1;
   else if (k == "max_batch") *value = h->max_batch;
   else if (k == "num_sms") *value = h->num_sms;
   else return fail("unknown option: " + k);

@@ -315,3 +315,36 @@ def test_module_tfrecord_intermediates_and_aggregation(tmp_path, shipped, monkey
     a = np.load(o.aggregated_classification_npz_output)
     assert list(a["contig_names"]) == list(names)
     assert np.array_equal(a["predictions"], agg.branch_attention(feats[:, 15:18].sum(1), mk, z["predictions"]))
+
+
+@pytest.mark.gpu
+def test_fused_layer1_wv_option(shipped):
+    """Option fuse_l1=1 (layer 1 + w_v#0 in one tcgen05 kernel whose B operand is written by SIMT producers in the TMA
+    swizzle layout) must reproduce the two separate kernels bit for bit: y1, q0 and the final probabilities, from ASCII
+    and from tokens, incl. N-rich / padded windows and a batch that leaves the last unit of every window partial."""
+    import torch
+    from genomad_b200.engine import Classifier
+    rng = np.random.default_rng(21)
+    n = 9
+    a = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (n, 6000))].copy()
+    a[1, 100:400] = ord("N"); a[2, 3000:] = ord("N"); a[3, :] = ord("N"); a[4, ::7] = ord("R")
+    at = torch.from_numpy(a).cuda()
+    clf = Classifier(max_batch=16)
+    tok = clf.encode(at)
+    res = {}
+    for f in (0, 1):
+        clf.set_option("fuse_l1", f)
+        n0 = clf.kernel_launches
+        p_ascii = clf.predict_ascii(at).cpu().numpy()
+        assert clf.kernel_launches - n0 == (17 if f else 18)
+        y1 = None
+        clf.set_option("debug_stop", 1)
+        clf.predict_ascii(at)
+        y1 = clf.debug_fetch("buf0", n).cpu().numpy()
+        q0 = clf.debug_fetch("q0", n).cpu().numpy()
+        clf.set_option("debug_stop", 0)
+        p_tok = clf.predict_tokens(tok).cpu().numpy()
+        res[f] = (p_ascii, p_tok, y1, q0)
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(res[1][0], res[1][1])
