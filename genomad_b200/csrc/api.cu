@@ -19,6 +19,7 @@
 #include "conv_ref.cuh"
 #include "igloo.cuh"
 #include "dense.cuh"
+#include "logits_tc.cuh"
 
 using namespace gnm;
 
@@ -72,6 +73,10 @@ struct gnm_handle {
   int ybuf_fp8lo[2] = {0, 0};                        // 1 = the buffer was written by conv2 (hi16 + lo8 + hi8 only)
   float* q[2] = {nullptr, nullptr};
   float* mpi[2] = {nullptr, nullptr};
+  float* mpi_hi[2] = {nullptr, nullptr}; float* mpi_lo[2] = {nullptr, nullptr};   // TF32 halves of mpi (logits_tc.cuh)
+  float* wqkT_hi[2] = {nullptr, nullptr}; float* wqkT_lo[2] = {nullptr, nullptr}; // TF32 halves of w_qk^T [749][2100]
+  CUtensorMap tm_lg_a[2][2];                         // [igloo][hi/lo] over mpi_hi / mpi_lo
+  CUtensorMap tm_lg_b[2][2];                         // [igloo][hi/lo] over wqkT_hi / wqkT_lo
   float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products
   float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
@@ -137,6 +142,19 @@ static int make_w_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
+  return 0;
+}
+
+// fp32 matrix [rows][inner] (row pitch = inner * 4 B), box = 32 floats (128 B) x box_rows, 128B swizzle, OOB -> 0
+static int make_f32_map(PFN_encodeTiled enc, CUtensorMap* tm, float* base, int inner, int rows, int box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(inner) * sizeof(float)};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(fp32 matrix) failed: " + std::to_string(int(r)));
   return 0;
 }
 
@@ -262,6 +280,15 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     if (dev_upload(h, &h->slot_of[s], slot_of.data(), slot_of.size())) return 1;
     if (dev_upload(h, &h->wbias[s], g.w_bias, kPatches)) return 1;
     if (dev_upload(h, &h->wqk[s], g.w_qk, static_cast<size_t>(kPatches) * kPooled)) return 1;
+    {   // w_qk^T [749][2100] as two TF32 halves: the K-major B operand of logits_tc_kernel
+      std::vector<float> thi(static_cast<size_t>(kPooled) * kPatches), tlo(thi.size());
+      for (int k = 0; k < kPatches; ++k)
+        for (int n = 0; n < kPooled; ++n)
+          split_tf32(g.w_qk[static_cast<size_t>(k) * kPooled + n], thi[static_cast<size_t>(n) * kPatches + k],
+                     tlo[static_cast<size_t>(n) * kPatches + k]);
+      if (dev_upload(h, &h->wqkT_hi[s], thi.data(), thi.size())) return 1;
+      if (dev_upload(h, &h->wqkT_lo[s], tlo.data(), tlo.size())) return 1;
+    }
     if (dev_upload(h, &h->wv32[s], g.w_v, static_cast<size_t>(kC) * kC)) return 1;
   }
   // ---- head: keras BN inference form  x * inv + (beta - mean * inv),  inv = gamma * rsqrt(var + eps)
@@ -291,6 +318,8 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     if (dev_alloc(h, &h->ybuf[i], mb * kTok * kRowBytes)) return 1;
     if (dev_alloc(h, &h->q[i], mb * kPooled * kC)) return 1;
     if (dev_alloc(h, &h->mpi[i], mb * kPatches)) return 1;
+    if (dev_alloc(h, &h->mpi_hi[i], mb * kPatches)) return 1;
+    if (dev_alloc(h, &h->mpi_lo[i], mb * kPatches)) return 1;
     if (dev_alloc(h, &h->in_stage[i], mb * kWindow)) return 1;
     if (dev_alloc(h, &h->out_stage[i], mb * 3)) return 1;
     GNM_CUDA(cudaEventCreateWithFlags(&h->in_ready[i], cudaEventDisableTiming));
@@ -300,7 +329,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   GNM_CUDA(cudaMemset(h->conv_dbg, 0, static_cast<size_t>(h->num_sms) * 8 * sizeof(long long)));
   if (dev_alloc(h, &h->part, mb * kGsSlots)) return 1;
   if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
-  if (dev_alloc(h, &h->logits_part, mb * kLogitsLd * 4)) return 1;
+  if (dev_alloc(h, &h->logits_part, mb * kLogitsLd * kLgSplits)) return 1;
   if (dev_alloc(h, &h->h0, mb * 256)) return 1;
   if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
   if (dev_alloc(h, &h->h2, mb * kHidden)) return 1;
@@ -318,12 +347,19 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[2], h->wpack[2], kWvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[3], h->wpack[3], kWvStages)) return 1;
+  for (int s = 0; s < 2; ++s) {
+    if (make_f32_map(enc, &h->tm_lg_a[s][0], h->mpi_hi[s], kPatches, max_batch, kLgBM)) return 1;
+    if (make_f32_map(enc, &h->tm_lg_a[s][1], h->mpi_lo[s], kPatches, max_batch, kLgBM)) return 1;
+    if (make_f32_map(enc, &h->tm_lg_b[s][0], h->wqkT_hi[s], kPatches, kPooled, kLgBN)) return 1;
+    if (make_f32_map(enc, &h->tm_lg_b[s][1], h->wqkT_lo[s], kPatches, kPooled, kLgBN)) return 1;
+  }
 
   // ---- opt in to large dynamic shared memory
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
   GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
+  GNM_CUDA(cudaFuncSetAttribute(logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<6>()));
   GNM_CUDA(cudaFuncSetAttribute(conv_ref_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ref_smem_bytes<1>()));
   GNM_CUDA(cudaDeviceSynchronize());
@@ -429,7 +465,7 @@ static int launch_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) 
   patch_stream_kernel<<<kGsGroups, kGsThreads, 0, st>>>(h->ybuf[buf], h->ent_pos[s], h->ent_w[s], h->part, n);
   if (check_launch(h, "patch_stream_kernel")) return 1;
   dim3 grid((kPatches + 255) / 256, n);
-  patch_finish_kernel<<<grid, 256, 0, st>>>(h->part, h->slot_of[s], h->wbias[s], h->mpi[s], n);
+  patch_finish_kernel<<<grid, 256, 0, st>>>(h->part, h->slot_of[s], h->wbias[s], h->mpi[s], h->mpi_hi[s], h->mpi_lo[s], n);
   return check_launch(h, "patch_finish_kernel");
 }
 
@@ -450,14 +486,27 @@ static int launch_sgemm(gnm_handle* h, const float* A, int lda, const float* B, 
 // ~5 CTAs on every SM; the partials are summed in fixed order by splitk_reduce_kernel.
 constexpr int kLogitsSplit = 4;
 static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
-  const int k_chunk = ((kPatches + kLogitsSplit - 1) / kLogitsSplit + kGemmBK - 1) / kGemmBK * kGemmBK;   // 528
-  dim3 grid((kPooled + kGemmBN - 1) / kGemmBN, (n + 63) / 64, kLogitsSplit);
-  sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(h->mpi[s], kPatches, h->wqk[s], kPooled, h->logits_part, kLogitsLd, n, kPooled,
-                                            kPatches, nullptr, nullptr, nullptr, 0, k_chunk);
-  if (check_launch(h, "sgemm_epi_kernel(split-K)")) return 1;
+  int parts;
+  if (h->conv_impl == 0) {
+    // tensor cores, 3 x TF32 (logits_tc.cuh): 3 N tiles x ceil(n/128) M tiles x 6 K splits
+    LogitsTcParams p;
+    p.part = h->logits_part; p.ldc = kLogitsLd; p.n_rows = n; p.n_cols = kPooled; p.status = h->status;
+    dim3 grid((kPooled + kLgBN - 1) / kLgBN, (n + kLgBM - 1) / kLgBM, kLgSplits);
+    logits_tc_kernel<<<grid, kLgThreads, kLgSmem, st>>>(h->tm_lg_a[s][0], h->tm_lg_a[s][1], h->tm_lg_b[s][0], h->tm_lg_b[s][1], p);
+    if (check_launch(h, "logits_tc_kernel")) return 1;
+    parts = kLgSplits;
+  } else {
+    // fp32 FFMA validation path (conv_impl = 1): 64x64 tiles, K split 4 ways
+    const int k_chunk = ((kPatches + kLogitsSplit - 1) / kLogitsSplit + kGemmBK - 1) / kGemmBK * kGemmBK;   // 528
+    dim3 grid((kPooled + kGemmBN - 1) / kGemmBN, (n + 63) / 64, kLogitsSplit);
+    sgemm_epi_kernel<64><<<grid, 256, 0, st>>>(h->mpi[s], kPatches, h->wqk[s], kPooled, h->logits_part, kLogitsLd, n, kPooled,
+                                              kPatches, nullptr, nullptr, nullptr, 0, k_chunk);
+    if (check_launch(h, "sgemm_epi_kernel(split-K)")) return 1;
+    parts = kLogitsSplit;
+  }
   const size_t total = static_cast<size_t>(n) * kLogitsLd;
   splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(h->logits_part, h->logits, n, kLogitsLd,
-                                                                                    kPooled, kLogitsSplit);
+                                                                                    kPooled, parts);
   return check_launch(h, "splitk_reduce_kernel");
 }
 

@@ -120,15 +120,21 @@ patch_stream_kernel(const uint8_t* __restrict__ y,         // [n][5997][768 B]; 
 }
 
 // mpi[w][p] = ((part[s0] + part[s1]) + part[s2]) + part[s3] + bias[p],  s_k = slot_of[4p + k]
+// Also writes the value's two TF32 halves (hi + lo, low 13 mantissa bits clear) for the tensor-core logits GEMM (logits_tc.cuh).
 __global__ void __launch_bounds__(256)
 patch_finish_kernel(const float* __restrict__ part, const int32_t* __restrict__ slot_of, const float* __restrict__ w_bias,
-                    float* __restrict__ mpi, int n_windows) {
+                    float* __restrict__ mpi, float* __restrict__ mpi_hi, float* __restrict__ mpi_lo, int n_windows) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = blockIdx.y;
   if (p >= kPatches) return;
   const float* pw = part + static_cast<size_t>(w) * kGsSlots;
   const int4 s4 = *reinterpret_cast<const int4*>(slot_of + p * 4);
-  mpi[static_cast<size_t>(w) * kPatches + p] = (((pw[s4.x] + pw[s4.y]) + pw[s4.z]) + pw[s4.w]) + w_bias[p];
+  const float v = (((pw[s4.x] + pw[s4.y]) + pw[s4.z]) + pw[s4.w]) + w_bias[p];
+  const size_t o = static_cast<size_t>(w) * kPatches + p;
+  mpi[o] = v;
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  mpi_hi[o] = hi;
+  mpi_lo[o] = __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -357,3 +357,31 @@ def test_native_fasta_property_random_texts(tmp_path):
         assert pf.check() == sequence.check_fasta(p)
 
     check()
+
+
+def test_tf32_three_pass_split_error_level():
+    """The tensor-core logits GEMM (csrc/logits_tc.cuh) multiplies TF32 halves: x = hi + lo with the low 13 mantissa bits of
+    both cleared, D = Ahi*Bhi + Alo*Bhi + Ahi*Blo.  NumPy emulation of exactly that split on a [64 x 2100] x [2100 x 749]
+    product: the error against float64 must stay at fp32-GEMM level (the plain fp32 product is the yardstick), including
+    for the ~1e-32 magnitudes of the shipped patch weights (TF32 keeps fp32's exponent range)."""
+    rng = np.random.default_rng(3)
+
+    def split(x):
+        x = x.astype(np.float32)
+        hi = (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = ((x - hi).astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    for scale_a, scale_b in ((1.0, 1.0), (50.0, 1e-3), (1e-31, 1e-31 * 1e25)):
+        a = (rng.standard_normal((64, 2100)) * scale_a).astype(np.float32)
+        b = (rng.standard_normal((2100, 749)) * scale_b).astype(np.float32)
+        exact = a.astype(np.float64) @ b.astype(np.float64)
+        ah, al = split(a)
+        bh, bl = split(b)
+        tc = ah @ bh + al @ bh + ah @ bl                       # products and sums in float64: isolates the split error
+        fp32 = (a @ b).astype(np.float64)
+        denom = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+        err_tc = (np.abs(tc - exact) / denom).max()
+        err_32 = (np.abs(fp32 - exact) / denom).max()
+        assert err_tc < 4e-6, (scale_a, scale_b, err_tc)       # 2^-20 + 2^-20 per product, before fp32 accumulation
+        assert err_tc < 40 * max(err_32, 1e-7)
