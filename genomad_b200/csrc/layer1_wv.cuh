@@ -24,7 +24,8 @@
 // but not yet faster, so it is OFF by default (option "fuse_l1").  Per 1024 windows, same-box A/B against 0.81 + 0.63 ms:
 //   16 producer warps x 8 rows, CTA-wide token buffer + barrier per unit, 2 rows in flight ............ 2.11 ms
 //   24 producer warps x 4 rows (96-position units), 8 table rows in flight per lane ................... 1.92 ms
-//   + warp-autonomous tokens (shuffles, next unit's bytes prefetched), no CTA barrier ................. 1.68 ms
+//   + warp-autonomous tokens (shuffles, next unit's bytes prefetched), no CTA barrier ................. 1.68 ms  <- this file
+//   + rolling two-row pipeline (next half-batch's table rows always in flight), hoisted address math ... 1.81 ms (not kept)
 // ~600 warp instructions per warp and unit (14.4 k per SM and unit = 3.6 k issue cycles of the 6.2 k the unit takes): the
 // producers are issue- and dependency-bound with 6 warps per scheduler, where the unfused layer-1 kernel has 16.  Next:
 // cut the per-row instruction count (uniform table indices, packed stores) or hand the row production to TMA-gather.
