@@ -40,7 +40,7 @@
 //     D^T[cout (M=128 TMEM lanes)][position (N=256 TMEM columns)] += W_tap^T[cout][cin] * Y[position + tap][cin]
 //
 //   A operand = one 16 KB weight stage, [128 cout][64 cin] fp16 or [128 cout][128 cin] e4m3, K-major
-//               SWIZZLE_128B (streamed by TMA through a 4-stage ring, host-packed in consumption order);
+//               SWIZZLE_128B (streamed by TMA through a 5-stage ring, host-packed in consumption order);
 //   B operand = 256 consecutive rows of one slab region.
 //
 // Schedule.  Weight stages are ordered region-major (all 6 taps against region 0, then region 1, ...) so a
