@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_w,
               const ConvTcParams p) {
   constexpr int kStagesU = kWvMode ? kWvStages : kConvStages;     // stages per unit
-  constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
+  constexpr uint32_t kIdescFull = umma_idesc_f16(128, 256);
+  // The last unit of a window holds only 5997 - 23 * 256 = 109 positions: N = 112 columns instead of 256 saves 56 % of that
+  // unit's tensor time (2.3 % of the kernel).  Columns 112.. of the accumulator then keep stale values; the epilogue never
+  // stores positions >= 5997 (conv) / pooled rows >= 749 (w_v), which is everything from column 109 on.
+  constexpr int kTailCols = ((kTok - (kUnitsPerWin - 1) * 2 * kTileM) + 15) / 16 * 16;          // 112
+  constexpr uint32_t kIdescTail = umma_idesc_f16(128, kTailCols);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_a = smem;                                   // activation slab: 4 regions x 272 rows x 128 B
@@ -184,6 +189,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       const uint32_t accphase = (it >> 1) & 1;
       const uint32_t aph = it & 1;
       const uint32_t acc = tmem_base + as * 256;
+      const uint32_t kIdesc = (unit % kUnitsPerWin == kUnitsPerWin - 1) ? kIdescTail : kIdescFull;
       tq = clock64();
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 200 + as);
       w_acc += clock64() - tq;
