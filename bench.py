@@ -116,12 +116,13 @@ def _cpu_cores() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_port_throughput(n_windows: int, batch: int, steps: int, warmup: int):
+def cpu_port_throughput(n_windows: int, batch: int, steps: int, warmup: int, budget_s: float = 0.0):
     """
     Time the oracle's op-for-op restatement of the reference graph (numpy tokenizer + one-hot -> conv1d -> IGLOO ...)
     on the host cores.  PyTorch's CPU conv does not scale to very wide hosts at this batch size, so the thread count
     is calibrated first (best of {all cores, 64, 32, 16} on a 16-window probe) -- the CPU arm gets its best setting.
-    Returns (windows/s, threads used, seconds per step).
+    With budget_s > 0 the per-step sample is shrunk (never below 8 windows) so that warmup + steps passes fit the budget
+    at the calibrated rate.  Returns (windows/s, threads used, seconds per step, windows per step).
     """
     import torch
     from oracle import igloo_model as M, tokenizer as T
@@ -140,6 +141,10 @@ def cpu_port_throughput(n_windows: int, batch: int, steps: int, warmup: int):
         if dt < best_t:
             best_threads, best_t = th, dt
     torch.set_num_threads(best_threads)
+    if budget_s > 0:
+        rate = 16 / best_t                                         # windows/s of the probe
+        n_windows = int(min(n_windows, max(8, budget_s * rate / max(1, steps + warmup))))
+        a = a[:n_windows]
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
@@ -149,23 +154,24 @@ def cpu_port_throughput(n_windows: int, batch: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
-    return n_windows * len(times) / sum(times), best_threads, float(np.mean(times))
+    return n_windows * len(times) / sum(times), best_threads, float(np.mean(times)), n_windows
 
 
 def run_reference_arm(args, rank: int):
     if rank != 0:
         return
-    n = 128                                                       # the reference's default --batch-size (cli.py:757-764)
-    value, cores, sec = cpu_port_throughput(n, 128, args.steps, args.warmup)
+    # one step = one pass over a bounded sample: at most 128 windows (the reference's default --batch-size, cli.py:757-764),
+    # fewer when --steps is large, so that the whole run stays within ~3 minutes of CPU time
+    value, cores, sec, n = cpu_port_throughput(128, 128, args.steps, args.warmup, budget_s=170.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] windows (6 kb, uniform ACGT), bounded sample: 128 windows per step",
+        "config": {"workload": f"BASELINE configs[1] windows (6 kb, uniform ACGT), bounded sample: {n} windows per step",
                    "note": "TensorFlow/Keras are not installable here; this is the oracle's op-for-op PyTorch-CPU "
                            "restatement of the Keras graph (one-hot conv1d as written) on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x 128 windows, encode + forward, torch {cores} threads "
+                         "sample": f"{args.steps} steps x {n} windows, encode + forward, torch {cores} threads "
                                    f"(best of the calibrated settings; host has {_cpu_cores()} cores)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -324,7 +330,7 @@ def main():
             "model_tflops_algorithmic": B * FLOP_DENSE_TOTAL / (total_ms / K * 1e-3) / 1e12,
         }
         if world == 1 and args.cpu_sample > 0:
-            v, cores, sec = cpu_port_throughput(args.cpu_sample, min(args.cpu_sample, 128), 1, 1)
+            v, cores, sec, _ = cpu_port_throughput(args.cpu_sample, min(args.cpu_sample, 128), 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_sample} windows (encode + op-for-op fp32 graph incl. one-hot conv1d), "
                                               f"1 warm-up + 1 timed pass, {sec:.1f} s, {cores} torch threads "
