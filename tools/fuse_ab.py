@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""A/B the opt-in fused layer-1 + w_v#0 kernel (option fuse_l1) against the two separate kernels on one box:
+per-stage times (ms per 1024 windows) and a bitwise comparison of the probabilities.  Usage: python tools/fuse_ab.py"""
 import sys
 from pathlib import Path
 import numpy as np, torch
