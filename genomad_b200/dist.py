@@ -61,6 +61,23 @@ def init_process_group_if_needed(backend: Optional[str] = None) -> DistInfo:
     return info
 
 
+def broadcast_object(obj, info: DistInfo, src: int = 0):
+    """Rank `src`'s Python object on every rank (no-op for a single process).  Used for control-flow decisions that
+    depend on the file system: only rank 0 looks, everybody follows."""
+    if info.world_size == 1:
+        return obj
+    import torch.distributed as dist
+    box = [obj if info.rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def barrier(info: DistInfo) -> None:
+    if info.world_size > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
 def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous, balanced block of [0, n_items) owned by `rank` (first n % world ranks get one extra)."""
     base, extra = divmod(n_items, world_size)

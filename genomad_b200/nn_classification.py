@@ -4,10 +4,12 @@
 (<prefix>_nn_classification.{log,json,tsv,npz}, <prefix>_encoded_sequences/, the provirus twins), same
 skip/restart/cleanup semantics, same error behaviour (message + sys.exit(1)).
 
-What changed underneath: the FASTA is parsed once by the native reader (csrc/fasta.cpp); its 6 kb windows
-are streamed through pinned chunks to the B200 (the host fills chunk i+1 while the GPU classifies chunk i),
-tokenised and classified by libgnm.so (hand-written sm_100a kernels) in steps of ``batch_size`` windows, and
-reduced per contig on the device.  TensorFlow, TFRecords and the per-batch ``predict`` call are gone; the
+What changed underneath: the FASTA is indexed once by the native reader (csrc/fasta.cpp: mmap, no copy); its 6 kb
+windows are streamed through pinned chunks to the B200 (the host fills chunk i+1 while the GPU classifies chunk i),
+tokenised and classified by libgnm.so (hand-written sm_100a kernels) and reduced per contig on the device.
+``--batch-size`` keeps the reference's meaning -- an upper bound on the memory one prediction step may use -- but no
+longer sets the device step: the library steps through >= 1024 windows at a time whatever the option says (the
+reference's default of 128 would pay the fixed per-step cost 8x as often for no benefit on a 180 GB part).  TensorFlow, TFRecords and the per-batch ``predict`` call are gone; the
 "encoded sequences" directory only records which window belongs to which sequence.  With torchrun (WORLD_SIZE > 1)
 windows are sharded across GPUs and combined over NCCL (genomad_b200.dist); rank 0 writes the outputs.
 """
@@ -26,10 +28,26 @@ from ._paths import NNOutputs
 _HEADER = "seq_name\tchromosome_score\tplasmid_score\tvirus_score\n"
 
 
+DEVICE_STEP_MIN, DEVICE_STEP_MAX = 1024, 4096
+_WORKSPACE_BYTES_PER_WINDOW = 7.0e6          # libgnm workspace per window of max_batch
+
+
+def device_step(batch_size: int, free_bytes: int) -> int:
+    """Windows per internal GPU step.  `--batch-size` (reference cli.py:757-764: "smaller value to reduce memory") only
+    bounds memory in the reference; here the step is max(batch_size, 1024) capped at 4096 -- throughput is flat from 512 up
+    (profiles/r01_batch_sweep.md) -- and halved until its workspace fits in half of the free HBM."""
+    step = min(DEVICE_STEP_MAX, max(DEVICE_STEP_MIN, int(batch_size)))
+    while step > 64 and step * _WORKSPACE_BYTES_PER_WINDOW > 0.5 * free_bytes:
+        step //= 2
+    return step
+
+
 def _make_classifier(batch_size: int, device: int):
     """Factory (patched in CPU tests): the real one needs a B200 and libgnm.so -- no fallback."""
+    import torch
     from .engine import Classifier
-    return Classifier(None, device=device, max_batch=max(1, int(batch_size)))
+    free, _total = torch.cuda.mem_get_info(device)
+    return Classifier(None, device=device, max_batch=device_step(batch_size, free))
 
 
 def _pinned_chunk(n: int):
@@ -41,11 +59,12 @@ def _pinned_chunk(n: int):
 
 def _classify_parsed(clf, parsed, offsets: np.ndarray, info: gdist.DistInfo, contig_reduce: str = "gather") -> np.ndarray:
     """
-    Parsed FASTA -> float32 [n_contigs, 3] per-contig mean (identical on all ranks).
+    Indexed FASTA -> float32 [n_contigs, 3] per-contig mean (identical on all ranks).
 
     This rank's contiguous block of the global window list is streamed in chunks: the native reader fills one pinned
-    chunk (upper-case + pad, multi-threaded) while the GPU classifies the previous one (gnm_classify_host on a worker
-    thread; the C call releases the GIL).  Windows never exist on disk.
+    chunk straight from the mmap'ed file (upper-case + pad, multi-threaded) while the GPU classifies the previous one
+    (gnm_classify_host on a worker thread; the C call releases the GIL) into a pinned result buffer, so neither copy
+    direction blocks the host.  Windows never exist on disk, and file pages behind the cursor are released.
     """
     import torch
     from concurrent.futures import ThreadPoolExecutor
@@ -53,20 +72,22 @@ def _classify_parsed(clf, parsed, offsets: np.ndarray, info: gdist.DistInfo, con
     start, end = gdist.shard_bounds(n, info.world_size, info.rank)
     chunk = max(4 * clf.max_batch, 4096)
     keep, bufs = zip(*(_pinned_chunk(min(chunk, max(1, end - start))) for _ in range(2)))
-    parts, futures = [], []
+    out_t = torch.empty((max(1, end - start), 3), dtype=torch.float32).pin_memory()
+    futures = []
     with ThreadPoolExecutor(max_workers=1) as gpu:
         for i, a in enumerate(range(start, end, chunk)):
             b = min(end, a + chunk)
             if i >= 2:
-                parts.append(futures[i - 2].result())            # buffer i%2 is free again
+                futures[i - 2].result()                          # buffer i%2 is free again
+                parsed.release_before(a - chunk)
             win = parsed.export_windows(a, b - a, bufs[i % 2])
-            futures.append(gpu.submit(clf.classify_host, win))
-        for f in futures[len(parts):]:
-            parts.append(f.result())
-    local = np.concatenate(parts) if parts else np.zeros((0, 3), np.float32)
+            futures.append(gpu.submit(clf.classify_host_into, win.ctypes.data, b - a,
+                                      out_t.data_ptr() + (a - start) * 12))
+        for f in futures:
+            f.result()
     del keep
     dev = torch.device("cuda", clf.device)
-    local_t = torch.from_numpy(local).to(dev)
+    local_t = out_t[: end - start].to(dev, non_blocking=True)
     if contig_reduce == "allreduce" and info.world_size > 1:
         loc_off = torch.from_numpy(gdist.local_offsets(offsets, start, end)).to(dev)
         partials = gdist.allreduce_partials(clf.segment_sum(local_t, loc_off), info.world_size)
@@ -151,11 +172,23 @@ def _encode_stage(console, enc_dir: Path, id_path: Path, names_key, ids_key, wha
     return index
 
 
-def main(input_path, output_path, single_window, batch_size, restart, threads, verbose, cleanup):
+def contig_reduce_mode(default: str = "gather") -> str:
+    """How per-contig means are combined when windows are sharded over GPUs (genomad_b200.dist): "gather" (default; outputs
+    bitwise independent of the number of GPUs) or "allreduce" (per-contig partial sums; for few, long contigs).
+    Chosen with GENOMAD_B200_CONTIG_REDUCE or main(..., contig_reduce=...)."""
+    mode = os.environ.get("GENOMAD_B200_CONTIG_REDUCE", default).strip().lower() or default
+    if mode not in ("gather", "allreduce"):
+        raise ValueError(f"GENOMAD_B200_CONTIG_REDUCE must be 'gather' or 'allreduce', not {mode!r}")
+    return mode
+
+
+def main(input_path, output_path, single_window, batch_size, restart, threads, verbose, cleanup, *, contig_reduce=None):
     input_path, output_path = Path(input_path), Path(output_path)
-    utils.start_md5(input_path)                          # hashed in the background while the file is parsed
     info = gdist.init_process_group_if_needed()
     is_main = info.is_main
+    contig_reduce = contig_reduce or contig_reduce_mode()
+    if is_main:
+        utils.start_md5(input_path)                      # hashed in the background while the file is indexed (rank 0 only)
     if not output_path.is_dir() and is_main:
         output_path.mkdir()
     prefix = input_path.stem
@@ -165,7 +198,10 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
     console = utils.HybridConsole(output_file=outputs.nn_classification_log if is_main else None,
                                   verbose=verbose and is_main)
     parameter_dict = {"single_window": single_window}
-    classify_proviruses = utils.check_provirus_execution(prefix, input_path, output_path)
+    # Every decision that depends on what is on disk is taken by rank 0 alone and broadcast: the other ranks never consult
+    # the file system for control flow (rank 0 rewrites the execution-info JSON and the outputs while they would look).
+    classify_proviruses = gdist.broadcast_object(
+        utils.check_provirus_execution(prefix, input_path, output_path) if is_main else None, info)
 
     files = [outputs.nn_classification_execution_info, outputs.encoded_sequences_dir,
              outputs.nn_classification_output, outputs.nn_classification_npz_output]
@@ -180,32 +216,42 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                          "This will classify the input sequences into chromosome, plasmid, or virus based on the "
                          "nucleotide sequence.", outputs.nn_classification_dir, files, descr)
 
-    parsed_input = sequence.ParsedFasta(input_path, single_window)      # one native pass: check + windows
+    parsed_input = sequence.ParsedFasta(input_path, single_window, threads)      # one native index pass: check + windows
     if not parsed_input.check():
         console.error(f"{input_path} is either empty or contains multiple entries with the same identifier. "
                       "Please check your input FASTA file and execute genomad nn-classification again.")
         sys.exit(1)
     console.log("Executing genomad nn-classification.")
 
-    skip = False
-    if outputs.nn_classification_execution_info.exists() and any(p.exists() for p in files) and not restart:
-        if utils.compare_executions(input_path, parameter_dict, outputs.nn_classification_execution_info):
-            skip = True
-            console.log("Previous execution detected. Steps will be skipped unless their outputs are not found. "
-                        "Use the --restart option to force the execution of all the steps again.")
-        else:
-            console.log("The input file or the parameters changed since the last execution. "
-                        "Previous outputs will be overwritten.")
-    if not outputs.nn_classification_dir.is_dir():
-        console.log(f"Creating the {outputs.nn_classification_dir} directory.")
-        if is_main:
-            outputs.nn_classification_dir.mkdir()
+    jobs = [("sequence", "contig", input_path, outputs.encoded_sequences_dir, outputs.seq_window_id_output,
+             "contig_names", "contig_ids", outputs.nn_classification_npz_output, outputs.nn_classification_output, True)]
+    if classify_proviruses:
+        jobs.append(("provirus", "provirus", outputs.find_proviruses_nucleotide_output, outputs.encoded_proviruses_dir,
+                     outputs.provirus_window_id_output, "provirus_names", "provirus_ids",
+                     outputs.provirus_nn_classification_npz_output, outputs.provirus_nn_classification_output, False))
+
+    plan = None
     if is_main:
+        skip = False
+        if outputs.nn_classification_execution_info.exists() and any(p.exists() for p in files) and not restart:
+            if utils.compare_executions(input_path, parameter_dict, outputs.nn_classification_execution_info):
+                skip = True
+                console.log("Previous execution detected. Steps will be skipped unless their outputs are not found. "
+                            "Use the --restart option to force the execution of all the steps again.")
+            else:
+                console.log("The input file or the parameters changed since the last execution. "
+                            "Previous outputs will be overwritten.")
+        if not outputs.nn_classification_dir.is_dir():
+            console.log(f"Creating the {outputs.nn_classification_dir} directory.")
+            outputs.nn_classification_dir.mkdir()
+        # per job: (skip the encoding stage, skip the classification) -- decided BEFORE anything is rewritten
+        plan = [(bool(skip and j[4].exists()), bool(skip and j[7].exists())) for j in jobs]
         utils.write_execution_info("nn_classification", input_path, parameter_dict,
                                    outputs.nn_classification_execution_info)
+    plan = gdist.broadcast_object(plan, info)
 
     # the classifier (CUDA context, weight upload, TMA descriptors: ~0.3 s) is built on a helper thread while the host
-    # parses; it is only joined when a job really has windows to classify
+    # indexes; it is only joined when a job really has windows to classify
     from concurrent.futures import ThreadPoolExecutor
     clf_pool = ThreadPoolExecutor(max_workers=1)
     clf_future = None
@@ -216,32 +262,28 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)
         return clf_future.result()
 
-    jobs = [("sequence", "contig", input_path, outputs.encoded_sequences_dir, outputs.seq_window_id_output,
-             "contig_names", "contig_ids", outputs.nn_classification_npz_output, outputs.nn_classification_output, True)]
-    if classify_proviruses:
-        jobs.append(("provirus", "provirus", outputs.find_proviruses_nucleotide_output, outputs.encoded_proviruses_dir,
-                     outputs.provirus_window_id_output, "provirus_names", "provirus_ids",
-                     outputs.provirus_nn_classification_npz_output, outputs.provirus_nn_classification_output, False))
-    if not (skip and all(j[7].exists() for j in jobs)):
-        clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)      # start now, overlap with parsing
+    if not all(cls_skip for _, cls_skip in plan):
+        clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)      # start now, overlap with indexing
 
-    for what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows in jobs:
-        need_classify = not (skip and npz_path.exists())
+    for (what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows), \
+            (enc_skip, cls_skip) in zip(jobs, plan):
         parsed = index = None
+        names = preds = None
         # ---- encode (here: record the window -> sequence map; the windows themselves are streamed to the GPU below)
-        if skip and id_path.exists():
+        if enc_skip:
             console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
         else:
-            parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window)
+            parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window, threads)
             index = _encode_stage(console, enc_dir, id_path, names_key, ids_key, what, is_main, parsed, classifier)
         # ---- classify
-        if not need_classify:
+        if cls_skip:
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")
-            z = np.load(npz_path)
-            names, preds = z[names_key], z["predictions"]
+            if is_main:
+                z = np.load(npz_path)
+                names, preds = z[names_key], z["predictions"]
         else:
             if parsed is None:
-                parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window)
+                parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window, threads)
                 index = parsed.index()
             if parsed.n_windows == 0:
                 if must_have_windows:
@@ -249,7 +291,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                     sys.exit(1)
                 names, preds = index.names, np.zeros((len(index.names), 3), np.float32)
             else:
-                preds = _classify_parsed(classifier(), parsed, index.offsets, info)
+                preds = _classify_parsed(classifier(), parsed, index.offsets, info, contig_reduce)
                 names = index.names
             console.log(f"{'Sequences' if what == 'sequence' else 'Proviruses'} classified.")
             if is_main:
@@ -257,7 +299,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             console.log(f"{noun.capitalize()} classification in binary format written to {npz_path.name}.")
         if parsed is not None:
             parsed.close()
-        if cleanup and enc_dir.is_dir() and is_main:
+        if cleanup and is_main and enc_dir.is_dir():
             console.log(f"Deleting encoded {what} data.")
             shutil.rmtree(enc_dir)
         if is_main:
@@ -265,4 +307,5 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
         console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
 
     clf_pool.shutdown(wait=True)
+    gdist.barrier(info)                                   # rank 0 has written everything before any rank returns
     console.log("geNomad nn-classification finished!")

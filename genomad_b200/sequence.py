@@ -16,9 +16,11 @@ vectors made with the real reference code (tests/golden/encoder_golden.json):
   * windows are upper-cased and right-padded with ``N`` to 6000 bytes (nn_classification.py:72).
 
 Unlike the reference (a Python generator of ``Sequence`` objects feeding a per-window numba call), the
-production path (``ParsedFasta`` / ``encode_fasta``) is native code in libgnm.so (csrc/fasta.cpp): one
-multi-threaded pass over the file text that writes one dense uint8 matrix [n_windows, 6000], which is shipped
-to the GPU as is -- tokenisation happens on the device (csrc/encode.cuh).  ``iter_fasta`` / ``window_spans`` /
+production path (``ParsedFasta`` / ``encode_fasta``) is native code in libgnm.so (csrc/fasta.cpp): a
+multi-threaded INDEX pass over the mmap'ed file (O(records) state, no copy), after which any block of the global
+window list is exported straight from the file text into pinned uint8 [n, 6000] chunks that are shipped to the
+GPU as they are -- tokenisation happens on the device (csrc/encode.cuh).  Compressed inputs are decompressed by
+Python's zlib/bz2/lzma bindings (C speed) into memory first.  ``iter_fasta`` / ``window_spans`` /
 ``encode_fasta_py`` are the readable pure-Python statement of the same rules; the tests hold the native code
 to them and both to golden vectors made with the real reference.
 """
@@ -175,12 +177,17 @@ class ParsedFasta:
         import os
         from . import engine
         self._lib = engine.load_library()
-        self._text = read_bytes(path)                       # kept alive: the parser points into it
-        self._threads = int(threads or min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8))
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self._threads = max(1, min(int(threads), avail)) if threads else min(32, avail)    # --threads is honoured
         self._h = C.c_void_p()
-        buf = self._text
-        rc = self._lib.gnm_fasta_parse(C.cast(C.c_char_p(buf), C.c_void_p), len(buf), int(bool(single_window)),
-                                       self._threads, C.byref(self._h))
+        if is_compressed(path) == Compression.uncompressed:
+            self._text = None                               # mmap inside the library: the file is never copied
+            rc = self._lib.gnm_fasta_open(str(path).encode(), int(bool(single_window)), self._threads, C.byref(self._h))
+        else:
+            self._text = read_bytes(path)                   # decompressed text, kept alive: the index points into it
+            buf = self._text
+            rc = self._lib.gnm_fasta_parse(C.cast(C.c_char_p(buf), C.c_void_p), len(buf), int(bool(single_window)),
+                                           self._threads, C.byref(self._h))
         if rc != 0:
             raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
         nrec, dup, nc, nw, hb = C.c_int64(), C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
@@ -233,6 +240,10 @@ class ParsedFasta:
                 raise RuntimeError(self._lib.gnm_fasta_last_error().decode())
         return out[:count]
 
+    def release_before(self, upto: int) -> None:
+        """mmap mode: drop the file pages that precede global window `upto` from the resident set."""
+        self._lib.gnm_fasta_release_before(self._h, int(upto))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.gnm_fasta_free(self._h)
@@ -246,9 +257,10 @@ class ParsedFasta:
             pass
 
 
-def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = None) -> EncodedFasta:
+def encode_fasta(path, single_window: bool = False, out: Optional[np.ndarray] = None,
+                 threads: Optional[int] = None) -> EncodedFasta:
     """FASTA -> dense window matrix (native)."""
-    p = ParsedFasta(path, single_window)
+    p = ParsedFasta(path, single_window, threads)
     try:
         return p.encode(out)
     finally:

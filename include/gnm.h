@@ -73,7 +73,7 @@ typedef struct gnm_weights {
 /* Thread-local description of the last failure on the calling thread. */
 const char* gnm_last_error(void);
 
-/* Library / build information, e.g. "libgnm 0.1 sm_100a". */
+/* Library / build information, e.g. "libgnm 0.3 (sm_100a; ...)". */
 const char* gnm_version(void);
 
 /*
@@ -127,23 +127,30 @@ int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_pro
 /* ---- host-side FASTA front end (no GPU involved) ------------------------------------------ */
 
 /*
- * FASTA text (already decompressed, `len` bytes, must stay alive until gnm_fasta_free) -> windows.
- * Replaces the Python loop read_fasta(strip_n=True) -> seq_windows(6000, 2500) -> N rule -> upper-case + pad
- * (sequence.py:96-167, nn_classification.py:65-72); multi-threaded, single pass over the text.
+ * FASTA -> windows, INDEX then STREAM (csrc/fasta.cpp).  Replaces the Python loop read_fasta(strip_n=True) ->
+ * seq_windows(6000, 2500) -> N rule -> upper-case + pad (sequence.py:96-167, nn_classification.py:65-72).
+ *   gnm_fasta_open   : plain (uncompressed) FASTA file; the file is mmap'ed, never copied into anonymous memory.
+ *   gnm_fasta_parse  : FASTA text in caller memory (decompressed input; `len` bytes, must stay alive until gnm_fasta_free).
+ *                      Both build the same multi-threaded index: O(records) state, no copy of the sequences.
  *   gnm_fasta_info   : n_records_nonempty / has_duplicate_ids are what check_fasta() tests (sequence.py:124-131);
  *                      n_contigs = records kept after stripping n/N; header_bytes = size of the headers export.
  *   gnm_fasta_export : windows uint8 [n_windows][6000] (may be pinned memory), offsets int32 [n_contigs + 1],
  *                      headers = the kept records' header lines joined with '\n' (header_bytes bytes); any pointer
  *                      may be NULL to skip that output.
+ *   gnm_fasta_export_windows : windows [first, first + count) of the GLOBAL window list -> dst uint8 [count][6000], straight
+ *                      from the text (any block, any order, `threads` threads): what a rank calls for its shard, chunk by chunk.
+ *   gnm_fasta_release_before : mmap mode only -- drop the mapped pages that lie before the record holding window `upto`
+ *                      from the resident set (they stay in the page cache).
  */
 typedef struct gnm_fasta gnm_fasta;
 const char* gnm_fasta_last_error(void);
+int gnm_fasta_open(const char* path, int single_window, int threads, gnm_fasta** out);
 int gnm_fasta_parse(const uint8_t* text, size_t len, int single_window, int threads, gnm_fasta** out);
 int gnm_fasta_info(const gnm_fasta* f, int64_t* n_records_nonempty, int* has_duplicate_ids, int64_t* n_contigs,
                    int64_t* n_windows, int64_t* header_bytes);
 int gnm_fasta_export(const gnm_fasta* f, uint8_t* windows, int32_t* offsets, char* headers, int threads);
-/* windows [first, first + count) of the global window list -> dst uint8 [count][6000] (streaming export) */
 int gnm_fasta_export_windows(const gnm_fasta* f, int64_t first, int64_t count, uint8_t* dst, int threads);
+int gnm_fasta_release_before(const gnm_fasta* f, int64_t upto);
 void gnm_fasta_free(gnm_fasta* f);
 
 /* ---- TFRecord files of tokenised windows (host side, no GPU involved; off by default) ------ */

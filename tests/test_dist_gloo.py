@@ -70,3 +70,75 @@ def test_local_offsets_straddling_contig():
     offsets = np.array([0, 167, 334, 501], np.int32)       # three 1 Mb contigs (167 windows each)
     assert gdist.local_offsets(offsets, 0, 251).tolist() == [0, 167, 251, 251]
     assert gdist.local_offsets(offsets, 251, 501).tolist() == [0, 0, 83, 250]
+
+
+# ------------------------------------------------------------------------------------------ module driver under 2 ranks
+class _Stub:
+    device = 0
+    max_batch = 64
+
+
+def _stub_classify(clf, parsed, offsets, info, contig_reduce="gather"):
+    """Stand-in for the GPU stage that keeps the real sharding + exchange (a collective: ranks that disagree on whether
+    to classify would hang here)."""
+    n = parsed.n_windows
+    s, e = gdist.shard_bounds(n, info.world_size, info.rank)
+    buf = np.zeros((max(1, e - s), 6000), np.uint8)
+    win = parsed.export_windows(s, e - s, buf)
+    x = win.astype(np.float64).sum(1)
+    local = torch.from_numpy(np.stack([np.sin(x) ** 2, np.cos(x) ** 2 / 2, np.cos(x) ** 2 / 2], 1).astype(np.float32))
+    full = gdist.gather_window_probs(local, n, info.world_size).numpy()
+    return T.segment_mean(full, np.repeat(np.arange(len(offsets) - 1), np.diff(offsets)), len(offsets) - 1)
+
+
+def _driver_worker(rank, world, port, tmp):
+    from pathlib import Path
+    from genomad_b200 import nn_classification, utils, _paths
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    gdist.init_process_group_if_needed("gloo")
+    nn_classification._make_classifier = lambda batch_size, device: _Stub()
+    nn_classification._classify_parsed = _stub_classify
+    if rank != 0:
+        # ranks other than 0 must not base control flow on the file system (ADVICE r1: skip-decision race)
+        def boom(*a, **k):
+            raise AssertionError("non-main rank consulted the file system for a control-flow decision")
+        utils.check_provirus_execution = boom
+        utils.compare_executions = boom
+        utils.get_md5 = boom
+    tmp = Path(tmp)
+    fa, out = tmp / "in.fna", tmp / "out"
+    o = _paths.NNOutputs("in", out)
+    nn_classification.main(fa, out, False, 128, False, 2, False, False)          # fresh run
+    if rank == 0:
+        first = np.load(o.nn_classification_npz_output)["predictions"].copy()
+    nn_classification.main(fa, out, False, 128, False, 2, False, False)          # skip run: nobody may enter the collective
+    dist.barrier()
+    if rank == 0:
+        assert "Skipping sequence classification" in o.nn_classification_log.read_text()
+        o.nn_classification_npz_output.unlink()                                   # rank 1 cannot know; rank 0 decides
+    dist.barrier()
+    nn_classification.main(fa, out, False, 128, False, 2, False, False)          # classification redone on BOTH ranks
+    nn_classification.main(fa, out, True, 128, True, 2, False, True)             # restart + parameter change + cleanup
+    if rank == 0:
+        z = np.load(o.nn_classification_npz_output)
+        assert z["predictions"].shape == first.shape and not o.encoded_sequences_dir.exists()
+        np.save(tmp / "first.npy", first)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_module_driver_rank0_decides(tmp_path):
+    rng = np.random.default_rng(2)
+    with open(tmp_path / "in.fna", "w") as fh:
+        for i, ln in enumerate([20000, 6100, 3000, 47000, 9000]):
+            s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, ln)].tobytes().decode()
+            fh.write(f">c{i}\n" + "\n".join(s[k:k + 70] for k in range(0, ln, 70)) + "\n")
+    mp.spawn(_driver_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    first = np.load(tmp_path / "first.npy")
+    # single-process run of the same stub pipeline gives the same per-contig means (sharding is invisible)
+    from genomad_b200 import sequence
+    pf = sequence.ParsedFasta(tmp_path / "in.fna")
+    idx = pf.index()
+    one = _stub_classify(_Stub(), pf, idx.offsets, gdist.DistInfo())
+    assert np.array_equal(first, one)

@@ -385,3 +385,41 @@ def test_tf32_three_pass_split_error_level():
         err_32 = (np.abs(fp32 - exact) / denom).max()
         assert err_tc < 4e-6, (scale_a, scale_b, err_tc)       # 2^-20 + 2^-20 per product, before fp32 accumulation
         assert err_tc < 40 * max(err_32, 1e-7)
+
+
+def test_native_fasta_streaming_block_export(tmp_path):
+    """Index-then-stream: any block of the global window list, in any order and with any thread count, equals the same rows
+    of the one-shot export -- for wrapped, single-line and ragged records, records that lose windows to the N rule, and
+    after gnm_fasta_release_before dropped the pages behind the cursor (they are re-read from the page cache)."""
+    rng = np.random.default_rng(11)
+    recs = []
+    for i, (ln, width) in enumerate([(61000, 60), (150000, 0), (7000, 80), (30011, 70), (45000, -1), (2600, 50), (90000, 61)]):
+        s = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.choice(9, ln, p=[.23, .23, .23, .23, .02, .02, .01, .01, .02])].copy()
+        if i == 3:
+            s[6000:10500] = ord("N")                       # window 1 is dropped (> 4000 N), later windows are kept
+        t = s.tobytes().decode()
+        if width == 0:
+            body = t                                        # one line
+        elif width < 0:                                     # ragged line lengths
+            cuts = np.cumsum(rng.integers(1, 200, 2000)); cuts = cuts[cuts < ln]
+            body = "\n".join(t[a:b] for a, b in zip(np.r_[0, cuts], np.r_[cuts, ln]))
+        else:
+            body = "\n".join(t[k:k + width] for k in range(0, ln, width))
+        recs.append(f">r{i} w={width}\n{body}\n")
+    p = tmp_path / "stream.fna"
+    p.write_text("".join(recs))
+    ref = sequence.encode_fasta_py(p)
+    pf = sequence.ParsedFasta(p, threads=3)
+    full = pf.encode()
+    assert np.array_equal(full.windows, ref.windows) and np.array_equal(full.offsets, ref.offsets)
+    n = pf.n_windows
+    assert n == ref.windows.shape[0] > 60
+    buf = np.zeros((17, 6000), np.uint8)
+    for first in list(rng.permutation(n))[:40] + [0, n - 1, n]:
+        cnt = int(min(rng.integers(0, 18), n - first))
+        got = pf.export_windows(int(first), cnt, buf)
+        assert np.array_equal(got, ref.windows[first:first + cnt])
+    pf.release_before(n // 2)
+    pf.release_before(n)
+    assert np.array_equal(pf.export_windows(0, 5, buf), ref.windows[:5])
+    pf.close()
