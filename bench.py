@@ -2,30 +2,43 @@
 """
 bench.py -- nn-classification throughput (6 kb windows/s) on N B200s, next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {1,2,3,4,5}] [--batch B] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" is one pass of the hot path (ASCII windows -> 4-mer tokens -> IGLOO1D classifier -> 3 class
-probabilities per window, reference genomad/modules/nn_classification.py:65-73,316-317) over one batch of
-1024 synthetic 6 kb windows per GPU -- BASELINE.json configs[1].  Prints ONE JSON line (rank 0).
+A "step" is one pass of the hot path (ASCII windows -> 4-mer tokens -> IGLOO1D classifier -> 3 class probabilities per
+window, reference genomad/modules/nn_classification.py:65-73,316-317) over one batch of synthetic 6 kb windows per GPU.
+Prints ONE JSON line (rank 0).  BASELINE.json's configs:
 
-  value  : windows/s with inputs already resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e    : the same metric through the host-buffer C-ABI call gnm_classify_host (pinned host buffers,
-           H2D of every step's windows and D2H of its probabilities inside the timed region)
+  --config 2 (default)  1 M x 6 kb windows (counter-based stream, genomad_b200/synth.py), batch 1024 per GPU: the headline.
+                        The line also carries `module_e2e` (FASTA -> TSV wall clock of nn_classification.main on config 1 and
+                        on a >= 100 k-window FASTA) and, at N > 1, `config4` (the long-contig FASTA through the module with
+                        both cross-GPU contig reducers).
+  --config 3            50 M windows sharded over N GPUs, batch 2048 per GPU (weak scaling; same timed loop, batch 2048).
+  --config 1            100 contigs x 10 kb through the module driver only (plumbing case).
+  --config 4            1,000 contigs x 1 Mb through the module driver with the `gather` and the `allreduce` reducer.
+  --config 5            batch sweep 256 ... 4096 with per-kernel HBM / tensor-pipe roofline fractions.
+
+  value    : windows/s with inputs already resident in HBM (CUDA events on the launching stream, max over ranks), after
+             >= 1.5 s of warm-up so the clock has settled under the 1 kW power cap (the burst figure is reported next to it)
+  e2e      : the same metric through the host-buffer C-ABI call gnm_classify_host (pinned host buffers, H2D of every
+             step's windows and D2H of its probabilities inside the timed region)
   roofline : the dominant kernel (tcgen05 Conv1D, conv_t_kernel<false>) against the measured bf16 tensor peak
   cpu_baseline : the oracle's op-for-op restatement of the Keras graph timed on this box's host cores
 
---impl reference times that CPU restatement (the reference's own implementation is TensorFlow, which cannot
-be installed here -- see DESIGN.md) with all host threads, on bounded 128-window steps.
+--impl reference times that CPU restatement (the reference's own implementation is TensorFlow, which cannot be installed
+here -- see DESIGN.md) with all host threads, on bounded 128-window steps.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import resource
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -40,6 +53,7 @@ UNIT = "6kb_windows/s"
 FLOP_CONV = 1_179_058_176        # per window per conv layer (2*5997*768*128), SURVEY.md section 8(d)
 FLOP_WV = 196_509_696            # per window per w_v projection (2*5997*128*128)
 FLOP_DENSE_TOTAL = 2 * FLOP_CONV + 2 * FLOP_WV
+STREAM_SEED = 1                  # BASELINE config 2: counter-based generator keyed by (seed = 1, window index)
 
 
 def load_peaks():
@@ -49,20 +63,6 @@ def load_peaks():
         return dict(tflops=float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), tflops_burst=float(d["bf16_tflops"]),
                     hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, bf16_tflops_sustained)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
-
-
-def synth_windows(n: int, seed: int, device):
-    """Counter-based synthetic windows generated on the device: uniform ACGT, 1 % of windows carry N runs / IUPAC."""
-    import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
-    a = lut[torch.randint(0, 4, (n, 6000), generator=g, device=device)]
-    dirty = torch.nonzero(torch.rand(n, generator=g, device=device) < 0.01).flatten().tolist()
-    for i in dirty:
-        s = int(torch.randint(0, 5500, (1,), generator=g, device=device))
-        a[i, s:s + 300] = ord("N")
-        a[i, (s * 7) % 6000] = ord("R")
-    return a
 
 
 class ClockSampler:
@@ -94,13 +94,13 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -108,7 +108,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": float(np.median(pw))}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
@@ -126,10 +127,10 @@ def cpu_port_throughput(n_windows: int, batch: int, steps: int, warmup: int, bud
     """
     import torch
     from oracle import igloo_model as M, tokenizer as T
+    from genomad_b200 import synth
     cores = _cpu_cores()
     w = M.load_npz_weights(ROOT / "genomad_b200" / "data" / "nn_classifier.npz")
-    rng = np.random.default_rng(1)
-    a = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (n_windows, 6000))]
+    a = synth.windows_numpy(np.arange(n_windows), seed=STREAM_SEED)          # the first windows of the config-2 stream
     probe = T.tokenize_windows(a[:16])
     best_threads, best_t = cores, float("inf")
     for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
@@ -167,9 +168,9 @@ def run_reference_arm(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1] windows (6 kb, uniform ACGT), bounded sample: {n} windows per step",
+        "config": {"workload": f"BASELINE configs[1] windows (6 kb, counter-based ACGT stream), bounded sample: {n} windows per step",
                    "note": "TensorFlow/Keras are not installable here; this is the oracle's op-for-op PyTorch-CPU "
-                           "restatement of the Keras graph (one-hot conv1d as written) on all host cores"},
+                           "restatement of the Keras graph (one-hot conv1d as written) on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {n} windows, encode + forward, torch {cores} threads "
                                    f"(best of the calibrated settings; host has {_cpu_cores()} cores)"},
@@ -179,15 +180,83 @@ def run_reference_arm(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------- synthetic FASTA files
+def write_fasta(path: Path, n_contigs: int, contig_len: int, seed: int = 0, line: int = 60, exact_rng: bool = False) -> int:
+    """Synthetic FASTA, `line` bases per line, ids contig_%0Nd.  exact_rng = BASELINE config 1's definition (every base drawn
+    from default_rng(seed)); otherwise contigs are rotations of a 16-sequence random pool (unique, ~10x faster to write)."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pool = None if exact_rng else [acgt[rng.integers(0, 4, contig_len)] for _ in range(16)]
+    width = max(3, len(str(n_contigs - 1)))
+    full, rest = divmod(contig_len, line)
+    with open(path, "wb") as fh:
+        for i in range(n_contigs):
+            s = acgt[rng.integers(0, 4, contig_len)] if exact_rng else np.roll(pool[i % 16], (i // 16) * 977 + i)
+            body = np.empty((full, line + 1), np.uint8)
+            body[:, :line] = s[:full * line].reshape(full, line)
+            body[:, line] = 10
+            fh.write(b">contig_%0*d\n" % (width, i))
+            fh.write(body.tobytes())
+            if rest:
+                fh.write(s[full * line:].tobytes() + b"\n")
+    return n_contigs
+
+
+def _tmp_root() -> Path:
+    shm = Path("/dev/shm")
+    base = shm if shm.is_dir() and os.access(shm, os.W_OK) and shutil.disk_usage(shm).free > 4e9 else Path(tempfile.gettempdir())
+    return base / f"gnm_bench_{os.getuid()}"
+
+
+def module_run(fasta: Path, out: Path, world: int, rank: int, dev, reducer: str = "gather", threads: int = 0):
+    """FASTA -> TSV through genomad_b200.nn_classification.main (the reference module's signature); wall clock on rank 0 between
+    barriers, windows/s = windows in the file / that time.  Includes md5, index, classifier construction, H2D/D2H, NPZ + TSV."""
+    import torch
+    import torch.distributed as dist
+    from genomad_b200 import nn_classification
+    threads = threads or max(1, _cpu_cores() // world)
+    if rank == 0 and out.exists():
+        shutil.rmtree(out)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nn_classification.main(fasta, out, False, 128, True, threads, False, True, contig_reduce=reducer)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    rss = torch.tensor([resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(rss, op=dist.ReduceOp.MAX)
+    res = None
+    if rank == 0:
+        prefix = fasta.stem
+        z = np.load(out / f"{prefix}_nn_classification" / f"{prefix}_nn_classification.npz")
+        n_contigs = int(z["predictions"].shape[0])
+        res = {"seconds": dt, "contigs": n_contigs, "file_mb": fasta.stat().st_size / 1e6, "host_threads_per_rank": threads,
+               "peak_rss_mb_max_over_ranks": float(rss.item()), "reducer": reducer,
+               "checksum": float(np.asarray(z["predictions"], np.float64).sum())}
+    return res
+
+
+def count_windows(contig_len: int, n_contigs: int) -> int:
+    full, rest = divmod(contig_len, 6000)
+    return n_contigs * max(1, full + (1 if rest >= 2500 else 0))
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config - 1]")
+    ap.add_argument("--batch", type=int, default=0, help="windows per GPU per step (default: 1024; 2048 for --config 3)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=64, help="windows in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-module", action="store_true", help="skip the module_e2e / config4 extras of the default line")
+    ap.add_argument("--module-windows", type=int, default=100_000, help="size of the large module_e2e FASTA (windows)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -200,7 +269,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from genomad_b200 import engine
+    from genomad_b200 import engine, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -208,38 +277,108 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, args.warmup
-    clf = engine.Classifier(None, device=local_rank, max_batch=B)
-
-    POOL = 4
-    pool = [synth_windows(B, seed=1000 * rank + i + 1, device=dev) for i in range(POOL)]
-    probs = torch.empty((B, 3), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * B, 3), dtype=torch.float32, device=dev) if world > 1 else None
-    host_in = [p.cpu().pin_memory() for p in pool]
-    host_out = torch.empty((B, 3), dtype=torch.float32).pin_memory()
-
-    def step_device(i):
-        clf.predict_ascii(pool[i % POOL], probs)
-        if world > 1:                                              # the one exchange step: gather per-window results
-            dist.all_gather_into_tensor(gathered, probs)
-
-    def step_host(i):
-        clf.classify_host_into(host_in[i % POOL].data_ptr(), B, host_out.data_ptr())
+    peaks = load_peaks()
+    tmp = _tmp_root()
+    if rank == 0:
+        tmp.mkdir(parents=True, exist_ok=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, use_events: bool):
-        for i in range(W):
-            fn(i)
+    # ------------------------------------------------------------------ module-level runs (configs 1 and 4, and the extras)
+    def module_case(name, n_contigs, contig_len, reducers=("gather",), exact_rng=False):
+        fasta = tmp / f"{name}.fna"
+        if rank == 0:
+            t0 = time.perf_counter()
+            write_fasta(fasta, n_contigs, contig_len, seed=0, exact_rng=exact_rng)
+            gen_s = time.perf_counter() - t0
+        barrier()
+        n_win = count_windows(contig_len, n_contigs)
+        out = {}
+        for red in reducers:
+            if name == "config1":                            # tiny case: one untimed run first (page cache, CUDA module load)
+                module_run(fasta, tmp / f"{name}_warm", world, rank, dev, red)
+            r = module_run(fasta, tmp / f"{name}_out_{red}", world, rank, dev, red)
+            if rank == 0:
+                r.update(windows=n_win, windows_per_s=n_win / r["seconds"], mbp_per_s=n_win * 0.006 / r["seconds"])
+                out[red] = r
+        barrier()
+        if rank == 0:
+            out["fasta"] = {"contigs": n_contigs, "contig_len": contig_len, "windows": n_win, "generate_s": gen_s}
+            if len(reducers) == 2:
+                a, b = (out[r]["checksum"] for r in reducers)
+                out["reducers_agree_abs"] = abs(a - b)
+            try:
+                fasta.unlink()
+                for red in reducers:
+                    shutil.rmtree(tmp / f"{name}_out_{red}", ignore_errors=True)
+                shutil.rmtree(tmp / f"{name}_warm", ignore_errors=True)
+            except OSError:
+                pass
+        return out
+
+    if args.config in (1, 4):
+        if args.config == 1:
+            res = module_case("config1", 100, 10_000, exact_rng=True)
+            key, workload = "gather", "BASELINE configs[0]: 100 synthetic 10 kb contigs (200 windows) through nn_classification.main, FASTA -> TSV"
+        else:
+            res = module_case("config4", 1000, 1_000_000, reducers=("gather", "allreduce"))
+            key, workload = "gather", ("BASELINE configs[3]: 1,000 contigs x 1 Mb (167,000 windows) through nn_classification.main, FASTA -> TSV; "
+                                       "contiguous window sharding -> contigs straddle ranks -> per-contig reduce across devices")
+        if rank == 0:
+            r = res[key]
+            line = {"metric": METRIC, "value": r["windows_per_s"], "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 0,
+                    "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "fp32-equivalent split operands (see --config 2 line)", "data": "synthetic",
+                    "config": {"workload": workload, "parallelism": f"window-sharded x{world}" if world > 1 else "single GPU"},
+                    "module": res}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    if args.config == 5:
+        run_sweep(args, rank, world, dev, peaks)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ configs 2 / 3: the timed step loop
+    B = args.batch or (2048 if args.config == 3 else 1024)
+    K, W = args.steps, args.warmup
+    clf = engine.Classifier(None, device=local_rank, max_batch=B)
+    total_windows = 50_000_000 if args.config == 3 else 1_000_000
+    shard = total_windows // world                       # rank r owns windows [r * shard, (r + 1) * shard) of the stream
+    POOL = 4
+    pool = [synth.windows_torch(rank * shard + i * B, B, STREAM_SEED, dev) for i in range(POOL)]
+    probs = [torch.empty((B, 3), dtype=torch.float32, device=dev) for _ in range(POOL)]
+    gathered = torch.empty((world * B * POOL, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    host_in = [p.cpu().pin_memory() for p in pool]
+    host_out = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+
+    def step_device(i):
+        clf.predict_ascii(pool[i % POOL], probs[i % POOL])
+
+    def exchange():                                      # the ONE exchange of a run (the module gathers per-window results once)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.cat(probs))
+
+    def step_host(i):
+        clf.classify_host_into(host_in[i % POOL].data_ptr(), B, host_out.data_ptr())
+
+    def timed(fn, use_events: bool, tail=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for i in range(K):
-            fn(W + i)
+            fn(i)
+        if tail is not None:
+            tail()
         e1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -249,13 +388,24 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = clf.kernel_launches
     step_device(0)
     per_step = clf.kernel_launches - l0                            # our kernels per step (counted, not assumed)
-    total_ms = timed(step_device, use_events=True)
+    for i in range(W):
+        step_device(i)
+    burst_ms = timed(step_device, use_events=True, tail=exchange)  # right after W warm-up steps: boost clock
+    # settle: keep stepping until >= 1.5 s have passed since the start, so `value` is the power-capped steady state
+    t_settle = time.perf_counter()
+    n_settle = 0
+    while time.perf_counter() - t_settle < 1.5:
+        for i in range(20):
+            step_device(i)
+        torch.cuda.synchronize()
+        n_settle += 20
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_device, use_events=True, tail=exchange)
     launches = per_step * K                                        # our kernels inside the K timed steps
     clocks = sampler.stop() if rank == 0 else None
 
@@ -270,38 +420,72 @@ def main():
     clf.set_option("profile_stages", 0)
     stage_ms = {k: float(np.mean(v)) for k, v in stages.items()}
 
+    for i in range(W):
+        step_host(i)
     e2e_ms = timed(step_host, use_events=False)
+    clf.check_status()
+
+    extras = {}
+    if args.config == 2 and not args.no_module:
+        clf.close()
+        del pool, probs
+        torch.cuda.empty_cache()
+        extras["module_e2e"] = {
+            "definition": "wall clock of genomad_b200.nn_classification.main(FASTA) -> TSV/NPZ written, incl. md5, index, classifier "
+                          "construction, host<->device copies; windows/s = windows in the file / seconds",
+            "config1_100x10kb": module_case("config1", 100, 10_000, exact_rng=True).get("gather"),
+        }
+        big_contigs = max(1, args.module_windows // 50)
+        extras["module_e2e"]["large_fasta"] = module_case("large", big_contigs, 300_000).get("gather")
+        if world > 1:
+            extras["config4"] = module_case("config4", 1000, 1_000_000, reducers=("gather", "allreduce"))
 
     if rank == 0:
-        peaks = load_peaks()
         value = world * B * K / (total_ms * 1e-3)
+        burst = world * B * K / (burst_ms * 1e-3)
         e2e = world * B * K / (e2e_ms * 1e-3)
         dom = "conv2"
         dom_ms = stage_ms.get(dom)
         dom_flop = B * FLOP_CONV
         achieved = dom_flop / (dom_ms * 1e-3) / 1e12 if dom_ms else None
-        traffic = None
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "ncu_traffic.json"
-        if tp.exists():
-            traffic = json.loads(tp.read_text()).get("conv2_dram_bytes_per_launch_batch1024")
+        if tp.exists() and B == 1024:
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("conv2_dram_bytes_per_launch_batch1024")
+            traffic_src = "static: " + tj.get("source", "ncu --set full capture, profiles/ncu_traffic.json") + " (not measured in this run)"
+
+        def hbm(key, gbytes, extra=None):
+            t = stage_ms.get(key)
+            d = {"bound": "hbm", "achieved": gbytes / (t * 1e-3) if t else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": gbytes / (t * 1e-3) / peaks["hbm_gbs"] if t else None, "algorithmic_gbytes_per_launch": gbytes, "launch_ms": t}
+            d.update(extra or {})
+            return d
+
+        rows_gb = B * 5997 * 512 / 1e9                          # hi16 + lo16 planes of every activation row, read ONCE
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "split operands on tcgen05 (conv: fp16 main pass + two e4m3 correction passes; w_v: 3 fp16 passes), fp32 accumulate; "
                      "fp32-equivalent (<=1e-4 vs the fp32 oracle, measured ~1e-5)", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 1M x 6 kb windows, batch 1024, IGLOO1D inference "
-                                   f"(timed: {K} steps of {B} windows/GPU from a device-resident pool of {POOL * B})",
+            "config": {"workload": (f"BASELINE configs[{args.config - 1}]: {total_windows:,} x 6 kb windows (counter-based stream, seed 1), "
+                                    f"batch {B} per GPU, IGLOO1D inference; timed: {K} steps of {B} windows per GPU "
+                                    f"(windows [r*{shard}, r*{shard}+{POOL * B}) of rank r's shard, device-resident)"),
                        "batch_per_gpu": B, "mbp_per_s": value * 0.006,
+                       "warmup_detail": f"{W} steps, then a burst measurement of {K} steps, then {n_settle} more untimed steps (>= 1.5 s) "
+                                        "before the timed region: `value` is the power-capped steady state",
+                       "value_burst": burst, "ms_per_step_burst": burst_ms / K,
                        "l2": "inputs rotate through a 4-batch pool; per-step activation working set "
                              f"{B * 5997 * 512 * 2 / 1e9:.1f} GB >> 126 MB L2 (no explicit flush needed)",
-                       "parallelism": f"window-sharded x{world}, all_gather of [B,3] per step" if world > 1 else "single GPU"},
+                       "parallelism": (f"window-sharded x{world}; ONE all_gather of the [windows,3] results per run, inside the timed "
+                                       "region (as the module does)") if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * 6000, "d2h_bytes_per_step": B * 12,
                     "ms_per_step": e2e_ms / K, "api": "gnm_classify_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_t_kernel<false> (causal Conv1D 128->128 k=6 + LeakyReLU, layer conv2; conv3 is the same kernel)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic,
+                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peaks["source"], "launch_ms": dom_ms,
                          "algorithmic_flop_per_launch": dom_flop,
                          "tensor_pass_units": 2.0,
@@ -311,24 +495,19 @@ def main():
                                  "bf16_equivalent_tflops = 2 x achieved is the figure comparable with the bf16 peak"},
             # HBM-bound stages against the measured copy bandwidth (algorithmic bytes per launch / launch time)
             "rooflines_hbm": {
-                name: {"bound": "hbm", "achieved": gb / (stage_ms[key] * 1e-3) if stage_ms.get(key) else None,
-                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": gb / (stage_ms[key] * 1e-3) / peaks["hbm_gbs"] if stage_ms.get(key) else None,
-                       "algorithmic_gbytes_per_launch": gb, **extra}
-                for name, key, gb, extra in (
-                    # SURVEY 8(d) counts every (patch, slot) row: 8400 x 512 B per window.  Only ~4510 of them are distinct
-                    # and repeats are served by L1, so the algorithmic figure can exceed the HBM peak; the DRAM-side
-                    # fraction uses the distinct rows (= what ncu measures as dram__bytes_read: 2.36 GB per launch).
-                    ("patch_stream_kernel (IGLOO patch gather, 8400 rows x 512 B per window)", "gather1", B * 4300800 / 1e9,
-                     {"distinct_rows_gbytes_per_launch": B * 4510 * 512 / 1e9,
-                      "frac_distinct_rows": (B * 4510 * 512 / 1e9) / (stage_ms["gather1"] * 1e-3) / peaks["hbm_gbs"]
-                      if stage_ms.get("gather1") else None,
-                      "note": "stage time includes the small patch_finish kernel"}),
-                    ("conv_t_kernel<true> (w_v + max-pool: reads hi16+lo16 planes once)", "wv1", B * (5997 * 512 + 749 * 512) / 1e9, {}),
-                    ("embed_conv1_kernel (encode + layer 1: writes four planes)", "embed_conv1", B * (6000 + 5997 * 768) / 1e9, {}))},
+                "wv_gather_kernel (IGLOO value projection + patch gather in ONE pass: reads the hi16+lo16 planes once, writes q + per-entry sums)":
+                    hbm("wvg1", rows_gb + B * (749 * 512 + 8400 * 4) / 1e9,
+                        {"gather_rows_served_per_launch_gbytes": B * 4300800 / 1e9,
+                         "note": "the 8,400 patch rows per window (4.3 MB, SURVEY 8d) are served from the same pass "
+                                 "(L2 hits next to the TMA stream), not from a second HBM sweep; stage time includes patch_finish_t_kernel"})
+                if "wvg1" in stage_ms else hbm("wv1", rows_gb + B * 749 * 512 / 1e9),
+                "embed_conv1_kernel (encode + layer 1: writes four planes)": hbm("embed_conv1", B * (6000 + 5997 * 768) / 1e9)},
             "stage_ms": stage_ms,
             "model_tflops_algorithmic": B * FLOP_DENSE_TOTAL / (total_ms / K * 1e-3) / 1e12,
         }
+        if "gather1" in stage_ms:
+            line["rooflines_hbm"]["patch_stream_kernel (distinct rows: 4510 x 512 B per window)"] = hbm("gather1", B * 4510 * 512 / 1e9)
+        line.update(extras)
         if world == 1 and args.cpu_sample > 0:
             v, cores, sec, _ = cpu_port_throughput(args.cpu_sample, min(args.cpu_sample, 128), 1, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -339,6 +518,55 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_sweep(args, rank, world, dev, peaks):
+    """BASELINE config 5's batch axis: windows/s and per-kernel roofline fractions at batch 128 ... 4096 (one line, key `sweep`)."""
+    import torch
+    import torch.distributed as dist
+    from genomad_b200 import engine, synth
+    rows = []
+    for B in (128, 256, 512, 1024, 2048, 4096):
+        clf = engine.Classifier(None, device=dev.index, max_batch=B)
+        pool = [synth.windows_torch(i * B, B, STREAM_SEED, dev) for i in range(3)]
+        out = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        K = max(8, 20480 // B)
+        for i in range(max(3, K // 2)):
+            clf.predict_ascii(pool[i % 3], out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            clf.predict_ascii(pool[i % 3], out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        clf.set_option("profile_stages", 1)
+        for i in range(4):
+            clf.predict_ascii(pool[i % 3], out)
+        torch.cuda.synchronize()
+        acc = {}
+        for name, t in clf.stage_times():
+            acc.setdefault(name, []).append(t)
+        st = {k: float(np.mean(v)) for k, v in acc.items()}
+        clf.close()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        big = {"embed_conv1", "conv2", "conv3", "wvg0", "wvg1", "wv0", "wv1", "gather0", "gather1"}
+        rows.append({"batch": B, "ms_per_step": ms, "windows_per_s": world * B / ms * 1e3,
+                     "conv2_frac_of_bf16_sustained": B * FLOP_CONV / (st["conv2"] * 1e-3) / 1e12 / peaks["tflops"],
+                     "wv_gather_frac_of_hbm": (B * (5997 * 512 + 749 * 512 + 33600) / 1e9) / (st["wvg1"] * 1e-3) / peaks["hbm_gbs"] if "wvg1" in st else None,
+                     "layer1_frac_of_hbm": (B * (6000 + 5997 * 768) / 1e9) / (st["embed_conv1"] * 1e-3) / peaks["hbm_gbs"],
+                     "small_kernels_ms": sum(v for k, v in st.items() if k not in big), "stage_ms": st})
+    if rank == 0:
+        best = max(rows, key=lambda r: r["windows_per_s"])
+        print(json.dumps({"metric": METRIC, "value": best["windows_per_s"], "unit": UNIT, "n_gpus": world, "steps": 0, "warmup": 0,
+                          "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "fp32-equivalent split operands", "data": "synthetic",
+                          "config": {"workload": "BASELINE configs[4] batch axis: batch sweep 128 ... 4096 per GPU (value = best row)"},
+                          "sweep": rows}), flush=True)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@
 #include "igloo.cuh"
 #include "dense.cuh"
 #include "logits_tc.cuh"
+#include "wv_gather.cuh"
 
 using namespace gnm;
 
@@ -36,7 +37,7 @@ static int fail(const std::string& m) { g_err = m; return 1; }
   } while (0)
 
 extern "C" const char* gnm_last_error(void) { return g_err.c_str(); }
-extern "C" const char* gnm_version(void) { return "libgnm 0.2 (sm_100a; tcgen05 fp16 + e4m3 split convs, fp16x3 w_v, tf32x3 logits)"; }
+extern "C" const char* gnm_version(void) { return "libgnm 0.3 (sm_100a; tcgen05 fp16 + e4m3 split convs, fp16x3 w_v, tf32x3 logits)"; }
 
 // ------------------------------------------------------------------------------------------------
 struct StageTimer {
@@ -54,6 +55,7 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
+  int fuse_gather = 1;      // 1 = w_v + patch gather in one pass over the activations (wv_gather.cuh); 0 = conv_t_kernel<true> + patch_stream_kernel
   int fuse_l1 = 0;          // 1 = layer 1 and w_v#0 in one kernel (layer1_wv.cuh; bit-identical, measured slower: off); 0 = embed_conv1_kernel + conv_t_kernel<true>
   long long* conv_dbg = nullptr;                    // [num_sms][8] cycle counters of the last conv_t_kernel<false> launch
   // weights on device
@@ -68,6 +70,10 @@ struct gnm_handle {
   float* d0w = nullptr; float* d0b = nullptr; float* bn0_scale = nullptr; float* bn0_shift = nullptr;
   float* d1w = nullptr; float* d1b = nullptr; float* bn1_scale = nullptr; float* bn1_shift = nullptr;
   float* d2w = nullptr; float* d2b = nullptr;
+  // tensor-core head (3 x TF32, logits_tc_kernel): transposed weights [512][K] and the activations as TF32 halves
+  float* dwT_hi[2] = {nullptr, nullptr}; float* dwT_lo[2] = {nullptr, nullptr};
+  float* hA_hi[2] = {nullptr, nullptr}; float* hA_lo[2] = {nullptr, nullptr};       // h0 [mb][256], h1 [mb][512]
+  CUtensorMap tm_hd_a[2][2]; CUtensorMap tm_hd_b[2][2];                              // [layer][hi/lo]
   // workspace
   uint8_t* ybuf[2] = {nullptr, nullptr};            // activation rows, 768 B per position
   int ybuf_fp8lo[2] = {0, 0};                        // 1 = the buffer was written by conv2 (hi16 + lo8 + hi8 only)
@@ -77,7 +83,10 @@ struct gnm_handle {
   float* wqkT_hi[2] = {nullptr, nullptr}; float* wqkT_lo[2] = {nullptr, nullptr}; // TF32 halves of w_qk^T [749][2100]
   CUtensorMap tm_lg_a[2][2];                         // [igloo][hi/lo] over mpi_hi / mpi_lo
   CUtensorMap tm_lg_b[2][2];                         // [igloo][hi/lo] over wqkT_hi / wqkT_lo
-  float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products
+  float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products ([kGsSlots][mb_pad] in the fused path)
+  int32_t* band_start[2] = {nullptr, nullptr};       // [kNumBands + 1] first entry slot of every 32-position band
+  int mb_pad = 0;                                    // max_batch rounded up to a multiple of 8 (window groups of wv_gather_kernel)
+  CUtensorMap tm_band[2];                            // activations, box = 128 B x 32 rows x 8 windows
   float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
@@ -121,10 +130,11 @@ static int get_encode_fn(PFN_encodeTiled* fn) {
 
 // activations [n][5997][768 B] viewed as bytes; box = 128 bytes (one plane slice) x 136 rows x 1 window, 128B swizzle,
 // rows outside [0, 5997) read as 0 (= causal padding)
-static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows) {
+static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows, int box_rows = kSlabRows,
+                        int box_windows = 1) {
   cuuint64_t dims[3] = {kRowBytes, kTok, static_cast<cuuint64_t>(n_windows)};
   cuuint64_t strides[2] = {kRowBytes, static_cast<cuuint64_t>(kTok) * kRowBytes};
-  cuuint32_t box[3] = {128, kSlabRows, 1};
+  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_windows)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -275,6 +285,16 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
       for (int c = 0; c < kC; ++c)
         ent_w[slot * kC + c] = (g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c]) * (1.f / kActScale);
     }
+    {
+      std::vector<int32_t> bs(kNumBands + 1, 0);             // ent_pos is sorted: band b = slots with position in [32b, 32b + 32)
+      size_t slot = 0;
+      for (int b = 0; b <= kNumBands; ++b) {
+        while (slot < order.size() && ent_pos[slot] < b * kBandRows) ++slot;
+        bs[b] = static_cast<int32_t>(slot);
+      }
+      bs[kNumBands] = static_cast<int32_t>(order.size());
+      if (dev_upload(h, &h->band_start[s], bs.data(), bs.size())) return 1;
+    }
     if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
     if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
     if (dev_upload(h, &h->slot_of[s], slot_of.data(), slot_of.size())) return 1;
@@ -309,13 +329,25 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     if (dev_upload(h, &h->d1w, w->dense1_kernel, static_cast<size_t>(kHidden) * kHidden)) return 1;
     if (dev_upload(h, &h->d1b, w->dense1_bias, kHidden)) return 1;
     if (bn(w->bn1, &h->bn1_scale, &h->bn1_shift)) return 1;
+    const float* dw[2] = {w->dense0_kernel, w->dense1_kernel};
+    const int dk[2] = {256, kHidden};
+    for (int L = 0; L < 2; ++L) {                          // W^T [512 out][K in] as two TF32 halves: the K-major B operand
+      std::vector<float> thi(static_cast<size_t>(kHidden) * dk[L]), tlo(thi.size());
+      for (int k = 0; k < dk[L]; ++k)
+        for (int n = 0; n < kHidden; ++n)
+          split_tf32(dw[L][static_cast<size_t>(k) * kHidden + n], thi[static_cast<size_t>(n) * dk[L] + k], tlo[static_cast<size_t>(n) * dk[L] + k]);
+      if (dev_upload(h, &h->dwT_hi[L], thi.data(), thi.size())) return 1;
+      if (dev_upload(h, &h->dwT_lo[L], tlo.data(), tlo.size())) return 1;
+    }
     if (dev_upload(h, &h->d2w, w->dense2_kernel, static_cast<size_t>(kHidden) * 3)) return 1;
     if (dev_upload(h, &h->d2b, w->dense2_bias, 3)) return 1;
   }
   // ---- workspace
   const size_t mb = static_cast<size_t>(max_batch);
+  h->mb_pad = (max_batch + kBandWins - 1) / kBandWins * kBandWins;
+  const size_t mbp = static_cast<size_t>(h->mb_pad);
   for (int i = 0; i < 2; ++i) {
-    if (dev_alloc(h, &h->ybuf[i], mb * kTok * kRowBytes)) return 1;
+    if (dev_alloc(h, &h->ybuf[i], mbp * kTok * kRowBytes)) return 1;      // whole window groups: wv_gather_kernel reads n_pad windows
     if (dev_alloc(h, &h->q[i], mb * kPooled * kC)) return 1;
     if (dev_alloc(h, &h->mpi[i], mb * kPatches)) return 1;
     if (dev_alloc(h, &h->mpi_hi[i], mb * kPatches)) return 1;
@@ -327,12 +359,16 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   }
   if (dev_alloc(h, &h->conv_dbg, static_cast<size_t>(h->num_sms) * 8)) return 1;
   GNM_CUDA(cudaMemset(h->conv_dbg, 0, static_cast<size_t>(h->num_sms) * 8 * sizeof(long long)));
-  if (dev_alloc(h, &h->part, mb * kGsSlots)) return 1;
+  if (dev_alloc(h, &h->part, mbp * kGsSlots)) return 1;
   if (dev_alloc(h, &h->logits, mb * kLogitsLd)) return 1;
   if (dev_alloc(h, &h->logits_part, mb * kLogitsLd * kLgSplits)) return 1;
   if (dev_alloc(h, &h->h0, mb * 256)) return 1;
   if (dev_alloc(h, &h->h1, mb * kHidden)) return 1;
   if (dev_alloc(h, &h->h2, mb * kHidden)) return 1;
+  if (dev_alloc(h, &h->hA_hi[0], mb * 256)) return 1;
+  if (dev_alloc(h, &h->hA_lo[0], mb * 256)) return 1;
+  if (dev_alloc(h, &h->hA_hi[1], mb * kHidden)) return 1;
+  if (dev_alloc(h, &h->hA_lo[1], mb * kHidden)) return 1;
   GNM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   GNM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
   GNM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->status), sizeof(DeviceStatus), cudaHostAllocMapped));
@@ -341,8 +377,10 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- TMA descriptors
   PFN_encodeTiled enc = nullptr;
   if (get_encode_fn(&enc)) return 1;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (make_act_map(enc, &h->tm_act[i], h->ybuf[i], max_batch)) return 1;
+    if (make_act_map(enc, &h->tm_band[i], h->ybuf[i], h->mb_pad, kBandRows, kBandWins)) return 1;
+  }
   if (make_w_map(enc, &h->tm_w[0], h->wpack[0], kConvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[2], h->wpack[2], kWvStages)) return 1;
@@ -354,9 +392,18 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
     if (make_f32_map(enc, &h->tm_lg_b[s][1], h->wqkT_lo[s], kPatches, kPooled, kLgBN)) return 1;
   }
 
+  for (int L = 0; L < 2; ++L) {
+    const int K = L == 0 ? 256 : kHidden;
+    if (make_f32_map(enc, &h->tm_hd_a[L][0], h->hA_hi[L], K, max_batch, kLgBM)) return 1;
+    if (make_f32_map(enc, &h->tm_hd_a[L][1], h->hA_lo[L], K, max_batch, kLgBM)) return 1;
+    if (make_f32_map(enc, &h->tm_hd_b[L][0], h->dwT_hi[L], K, kHidden, kLgBN)) return 1;
+    if (make_f32_map(enc, &h->tm_hd_b[L][1], h->dwT_lo[L], K, kHidden, kLgBN)) return 1;
+  }
+
   // ---- opt in to large dynamic shared memory
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
   GNM_CUDA(cudaFuncSetAttribute(conv_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTSmem));
+  GNM_CUDA(cudaFuncSetAttribute(wv_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
   GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
   GNM_CUDA(cudaFuncSetAttribute(layer1_wv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
   GNM_CUDA(cudaFuncSetAttribute(logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLgSmem));
@@ -434,6 +481,25 @@ static int launch_wv_tc(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   return check_launch(h, "conv_t_kernel<true>");
 }
 
+// IGLOO kernel s on y[buf]: q[s] = maxpool8(y @ w_v#s) and mpi[s] (patch gather) in ONE pass over the activations
+static int launch_wv_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
+  WvGatherParams p;
+  p.q_out = h->q[s]; p.out_scale = 1.f / kActScale;
+  p.ent_pos = h->ent_pos[s]; p.ent_w = h->ent_w[s]; p.band_start = h->band_start[s]; p.part_t = h->part;
+  p.n_windows = n;
+  p.n_pad = (n + kBandWins - 1) / kBandWins * kBandWins;
+  p.groups = p.n_pad / kBandWins;
+  p.n_units = kNumBands * p.groups;
+  p.status = h->status;
+  p.experiment = h->conv_experiment;
+  const int grid = std::min(h->num_sms, p.n_units);
+  wv_gather_kernel<<<grid, kWgThreads, kWgSmem, st>>>(h->tm_band[buf], h->tm_w[2 + s], p);
+  if (check_launch(h, "wv_gather_kernel")) return 1;
+  dim3 fgrid((kPatches + 31) / 32, (n + 31) / 32);
+  patch_finish_t_kernel<<<fgrid, 256, 0, st>>>(h->part, h->slot_of[s], h->wbias[s], h->mpi[s], h->mpi_hi[s], h->mpi_lo[s], n, p.n_pad);
+  return check_launch(h, "patch_finish_t_kernel");
+}
+
 static int ensure_scratch(gnm_handle* h) {
   if (h->scratch32) return 0;
   GNM_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->scratch32), static_cast<size_t>(h->max_batch) * kTok * kC * sizeof(float)));
@@ -491,6 +557,7 @@ static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
     // tensor cores, 3 x TF32 (logits_tc.cuh): 3 N tiles x ceil(n/128) M tiles x 6 K splits
     LogitsTcParams p;
     p.part = h->logits_part; p.ldc = kLogitsLd; p.n_rows = n; p.n_cols = kPooled; p.status = h->status;
+    p.chunks_total = kLgChunks; p.chunks_per_split = kLgChunksPerSplit;
     dim3 grid((kPooled + kLgBN - 1) / kLgBN, (n + kLgBM - 1) / kLgBM, kLgSplits);
     logits_tc_kernel<<<grid, kLgThreads, kLgSmem, st>>>(h->tm_lg_a[s][0], h->tm_lg_a[s][1], h->tm_lg_b[s][0], h->tm_lg_b[s][1], p);
     if (check_launch(h, "logits_tc_kernel")) return 1;
@@ -508,6 +575,29 @@ static int launch_logits(gnm_handle* h, int s, int n, cudaStream_t st) {
   splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(h->logits_part, h->logits, n, kLogitsLd,
                                                                                     kPooled, parts);
   return check_launch(h, "splitk_reduce_kernel");
+}
+
+// Dense(512) + BatchNorm + ReLU of the head on the tensor cores: out = relu(bn(A @ W + b)), A given as TF32 halves (layer 0: h0
+// [n][256] written by attention_kernel, layer 1: h1 [n][512] written by the previous call), 3 x TF32 passes, K split 8 ways so
+// 128 CTAs run at batch 1024; the split-K partials go through logits_part (6 x 752 floats per window >= 8 x 512).
+constexpr int kHeadSplits = 8;
+static_assert(kHeadSplits * kHidden <= kLgSplits * kLogitsLd, "logits_part is too small for the head's split-K partials");
+static int launch_dense_tc(gnm_handle* h, int layer, int n, float* out, float* out_hi, float* out_lo, cudaStream_t st) {
+  const int K = layer == 0 ? 256 : kHidden;
+  LogitsTcParams p;
+  p.part = h->logits_part; p.ldc = kHidden; p.n_rows = n; p.n_cols = kHidden; p.status = h->status;
+  p.chunks_total = K / kLgBK;
+  p.chunks_per_split = (p.chunks_total + kHeadSplits - 1) / kHeadSplits;
+  const int splits = (p.chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
+  dim3 grid(kHidden / kLgBN, (n + kLgBM - 1) / kLgBM, splits);
+  logits_tc_kernel<<<grid, kLgThreads, kLgSmem, st>>>(h->tm_hd_a[layer][0], h->tm_hd_a[layer][1], h->tm_hd_b[layer][0],
+                                                      h->tm_hd_b[layer][1], p);
+  if (check_launch(h, "logits_tc_kernel(dense)")) return 1;
+  const size_t total = static_cast<size_t>(n) * kHidden;
+  splitk_reduce_epi_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      h->logits_part, out, out_hi, out_lo, n, kHidden, splits, layer == 0 ? h->d0b : h->d1b,
+      layer == 0 ? h->bn0_scale : h->bn1_scale, layer == 0 ? h->bn0_shift : h->bn1_shift, 1);
+  return check_launch(h, "splitk_reduce_epi_kernel");
 }
 
 // One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
@@ -528,16 +618,22 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   } else {
   timer_mark(h, "embed_conv1", st);
   if (d_ascii)
-    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
+    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status, h->conv_experiment);
   else
-    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n);
+    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status, h->conv_experiment);
   if (check_launch(h, "embed_conv1_kernel")) return 1;
   }
-  timer_mark(h, "gather0", st);
-  if (launch_gather(h, 0, 0, n, st)) return 1;
+  const bool fg = h->fuse_gather && h->conv_impl == 0 && !fused;     // w_v + gather in one kernel (wv_gather.cuh)
+  if (fg) {
+    timer_mark(h, "wvg0", st);
+    if (launch_wv_gather(h, 0, 0, n, st)) return 1;          // y1 (buf0) -> q0, mpi0
+  } else {
+    timer_mark(h, "gather0", st);
+    if (launch_gather(h, 0, 0, n, st)) return 1;
+  }
   if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
   if (h->conv_impl == 0) {
-    if (!fused) {
+    if (!fused && !fg) {
       timer_mark(h, "wv0", st);
       if (launch_wv_tc(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> q0
     }
@@ -547,8 +643,13 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     timer_mark(h, "conv3", st);
     if (launch_conv(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
     if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
-    timer_mark(h, "wv1", st);
-    if (launch_wv_tc(h, 1, 0, n, st)) return 1;               // y3 (buf0) -> q1
+    if (fg) {
+      timer_mark(h, "wvg1", st);
+      if (launch_wv_gather(h, 1, 0, n, st)) return 1;        // y3 (buf0) -> q1, mpi1
+    } else {
+      timer_mark(h, "wv1", st);
+      if (launch_wv_tc(h, 1, 0, n, st)) return 1;               // y3 (buf0) -> q1
+    }
   } else {
     timer_mark(h, "wv0(ref)", st);
     if (launch_wv_ref(h, 0, 0, n, st)) return 1;
@@ -561,18 +662,25 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     timer_mark(h, "wv1(ref)", st);
     if (launch_wv_ref(h, 1, 0, n, st)) return 1;
   }
-  timer_mark(h, "gather1", st);
-  if (launch_gather(h, 1, 0, n, st)) return 1;
+  if (!fg) {
+    timer_mark(h, "gather1", st);
+    if (launch_gather(h, 1, 0, n, st)) return 1;
+  }
   for (int s = 0; s < 2; ++s) {
     timer_mark(h, s ? "logits1" : "logits0", st);
     if (launch_logits(h, s, n, st)) return 1;
     timer_mark(h, s ? "attention1" : "attention0", st);
-    attention_kernel<<<n, 128, 0, st>>>(h->logits, h->q[s], h->h0, s * kC);
+    attention_kernel<<<n, 128, 0, st>>>(h->logits, h->q[s], h->h0, h->hA_hi[0], h->hA_lo[0], s * kC);
     if (check_launch(h, "attention_kernel")) return 1;
   }
   timer_mark(h, "head", st);
-  if (launch_sgemm(h, h->h0, 256, h->d0w, kHidden, h->h1, kHidden, n, kHidden, 256, h->d0b, h->bn0_scale, h->bn0_shift, 1, st)) return 1;
-  if (launch_sgemm(h, h->h1, kHidden, h->d1w, kHidden, h->h2, kHidden, n, kHidden, kHidden, h->d1b, h->bn1_scale, h->bn1_shift, 1, st)) return 1;
+  if (h->conv_impl == 0) {       // tensor cores, 3 x TF32 (the model's dense projections; the FFMA kernels stay the validation path)
+    if (launch_dense_tc(h, 0, n, h->h1, h->hA_hi[1], h->hA_lo[1], st)) return 1;
+    if (launch_dense_tc(h, 1, n, h->h2, nullptr, nullptr, st)) return 1;
+  } else {
+    if (launch_sgemm(h, h->h0, 256, h->d0w, kHidden, h->h1, kHidden, n, kHidden, 256, h->d0b, h->bn0_scale, h->bn0_shift, 1, st)) return 1;
+    if (launch_sgemm(h, h->h1, kHidden, h->d1w, kHidden, h->h2, kHidden, n, kHidden, kHidden, h->d1b, h->bn1_scale, h->bn1_shift, 1, st)) return 1;
+  }
   dense3_softmax_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(h->h2, h->d2w, h->d2b, d_probs, n);
   if (check_launch(h, "dense3_softmax_kernel")) return 1;
   timer_mark(h, "end", st);
@@ -580,6 +688,15 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
 }
 
 static int check_device_status(gnm_handle* h) {
+  if (h->status && h->status->act_overflow) {
+    // not fatal for the device, but the parity promise no longer holds for the step that raised it: fail loudly
+    const int stage = h->status->ov_stage[1] ? 1 : h->status->ov_stage[2] ? 2 : 3;       // the first layer that left the range
+    h->status->act_overflow = 0;
+    for (int i = 0; i < 4; ++i) h->status->ov_stage[i] = 0;
+    return fail(std::string("activation range exceeded in ") + (stage == 1 ? "layer 1" : stage == 2 ? "conv2" : "conv3") +
+                ": |y| > 3.5 saturates the e4m3 correction plane (|y| > 2047 overflows fp16) -- these weights are outside the "
+                "range the split-operand tensor-core recipe supports (common.cuh); results of that step are not within 1e-4");
+  }
   if (h->status && h->status->code != kDevOk) {
     char buf[160];
     std::snprintf(buf, sizeof buf, "device-side failure %d (mbarrier timeout) tag=%d block=%d thread=%d",
@@ -653,6 +770,15 @@ extern "C" int gnm_segment_sum(gnm_handle* h, const float* d_probs, const int32_
   return segment_any(h, d_probs, d_offsets, n_contigs, d_sum4, stream, false);
 }
 
+// Wait for the work queued on `stream` and report device-side failures of the steps run so far (mbarrier time-outs,
+// activation range overflow).  The asynchronous entry points only see such a flag on the NEXT call.
+extern "C" int gnm_check_status(gnm_handle* h, void* stream) {
+  if (!h) return fail("null handle");
+  GNM_CUDA(cudaSetDevice(h->device));
+  GNM_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return check_device_status(h);
+}
+
 // Host buffers in, host buffers out; H2D of step i+1 overlaps compute of step i.
 extern "C" int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_probs) {
   if (!h) return fail("null handle");
@@ -689,6 +815,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   else if (k == "debug_stop") h->debug_stop = value;
   else if (k == "conv_experiment") h->conv_experiment = value;
   else if (k == "fuse_l1") h->fuse_l1 = value ? 1 : 0;
+  else if (k == "fuse_gather") h->fuse_gather = value ? 1 : 0;
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
   return 0;
@@ -700,6 +827,7 @@ extern "C" int gnm_get_option(gnm_handle* h, const char* name, int* value) {
   else if (k == "debug_stop") *value = h->debug_stop;
   else if (k == "profile_stages") *value = h->profile_stages;
   else if (k == "fuse_l1") *value = h->fuse_l1;
+  else if (k == "fuse_gather") *value = h->fuse_gather;
   else if (k == "max_batch") *value = h->max_batch;
   else if (k == "num_sms") *value = h->num_sms;
   else return fail("unknown option: " + k);

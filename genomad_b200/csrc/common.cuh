@@ -22,7 +22,10 @@ constexpr int kHidden   = 512;    // dense width                       (referenc
 constexpr float kLeaky  = 0.1f;   // LeakyReLU slope                   (reference igloo.py:48,67)
 
 // Activation row in HBM: 768 bytes per position.  With Y = 32 * y (kActScale keeps the fp16 "lo" part and the fp8
-// planes away from their subnormal ranges; |y| may reach 2047 before fp16 overflows):
+// planes away from their subnormal ranges).  Range: the e4m3 plane hi8 = hi16 * 4 saturates (SATFINITE, 448) once
+// |Y| > 112, i.e. |y| > 3.5 -- the Ahi*Wlo correction pass of the next conv would then be wrong and precision would fall
+// back to the single-pass level (~1.3e-4) -- and fp16 itself overflows at |y| > 2047.  Producers check both limits and raise
+// DeviceStatus::act_overflow (reported by the next API call as an error); the shipped model stays below |y| = 0.7.
 //   [  0,256)  hi16 = fp16(Y)                       128 halves   -- main tensor-core operand, w_v, patch gather
 //   [256,512)  lo16 = fp16(Y - hi16)                128 halves   -- w_v 3-pass split, patch gather
 //   [512,640)  lo8  = e4m3((Y - hi16) * 128)        128 bytes    -- conv correction pass  lo(A) * hi(W)
@@ -32,6 +35,8 @@ constexpr int kOffHi16   = 0, kOffLo16 = 256, kOffLo8 = 512, kOffHi8 = 640;
 constexpr float kActScale = 32.f;          // 2^5
 constexpr float kLo8Scale = 128.f;         // lo8 = (Y - hi16) * 2^7   -> y_lo * 2^12
 constexpr float kHi8Scale = 4.f;           // hi8 = hi16 * 2^2         -> y_hi * 2^7
+constexpr float kHi8Limit = 448.f / kHi8Scale;   // |Y| above this saturates the hi8 plane   (|y| > 3.5)
+constexpr float kF16Limit = 65504.f;             // |Y| above this overflows the hi16 plane  (|y| > 2047)
 
 // ----------------------------------------------------------------------------- small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -62,8 +67,12 @@ __device__ __forceinline__ uint16_t pack_e4m3x2(float a, float b) {
 }
 
 // error flag written by device-side timeouts (see mbar_wait); checked by the host API
-struct DeviceStatus { int code; int info0; int info1; int info2; };
+struct DeviceStatus { int code; int info0; int info1; int info2; int act_overflow; int ov_stage[4]; };
 enum : int { kDevOk = 0, kDevMbarTimeout = 1 };
+// activation range check (see the row layout above): stage = 1 layer 1, 2 conv2, 3 conv3
+__device__ __forceinline__ void flag_act_overflow(DeviceStatus* st, float absmax, float limit, int stage) {
+  if (absmax > limit && st) { st->act_overflow = 1; st->ov_stage[stage] = 1; }
+}
 
 // exactly one lane of a fully converged warp gets true (PTX elect.sync); ptxas then keeps the
 // guarded tcgen05/TMA instructions on the uniform datapath instead of a per-lane waterfall loop
@@ -106,8 +115,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DeviceStatus* st, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+  for (uint32_t spins = 1;; ++spins) {
+    if (mbar_try_wait(bar, parity)) return;          // try_wait itself suspends the thread for a hardware-defined time slice
+    if ((spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz; the clock is read once per 256 spins
       if (st) { st->code = kDevMbarTimeout; st->info0 = tag; st->info1 = blockIdx.x; st->info2 = threadIdx.x; }
       __threadfence_system();
       __trap();

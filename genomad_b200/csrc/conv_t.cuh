@@ -89,7 +89,7 @@ struct ConvTcParams {
   float out_scale;          // conv: 2^-S (undoes the common operand scaling); w_v: 1/32 (activation scale)
   int out_fp8;              // conv: 1 = write hi16 + lo8 + hi8 (consumer is a conv), 0 = write hi16 + lo16
   int n_tiles;              // number of work units = n_windows * 24
-  int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores
+  int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores, 16 = no hi8-plane stores
   long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
   DeviceStatus* status;
 };
@@ -257,6 +257,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
     const float bias = kWvMode ? 0.f : p.bias[ch];
     const float oscale = p.out_scale;
     int it = 0;
+    float amax = 0.f;                                          // largest |Y| this thread produced (range check, common.cuh)
     long long w_full_c = 0, tq;
     const long long t_begin = clock64();
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
@@ -296,6 +297,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
             for (int i = 0; i < 32; i += 2) {
               const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
               const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
+              amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
               const __half2 h = __floats2half2_rn(y0, y1);
               const float2 f = __half22float2(h);
               const uint16_t lo = pack_e4m3x2((y0 - f.x) * kLo8Scale, (y1 - f.y) * kLo8Scale);
@@ -304,13 +306,13 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
                 uint8_t* q = rowp + i * kRowBytes;
                 reinterpret_cast<__half*>(q + kOffHi16)[ch] = __low2half(h);
                 q[kOffLo8 + ch] = static_cast<uint8_t>(lo & 0xff);
-                q[kOffHi8 + ch] = static_cast<uint8_t>(hi & 0xff);
+                if (!(p.experiment & 16)) q[kOffHi8 + ch] = static_cast<uint8_t>(hi & 0xff);
               }
               if (store && p0 + i + 1 < kTok) {
                 uint8_t* q = rowp + (i + 1) * kRowBytes;
                 reinterpret_cast<__half*>(q + kOffHi16)[ch] = __high2half(h);
                 q[kOffLo8 + ch] = static_cast<uint8_t>(lo >> 8);
-                q[kOffHi8 + ch] = static_cast<uint8_t>(hi >> 8);
+                if (!(p.experiment & 16)) q[kOffHi8 + ch] = static_cast<uint8_t>(hi >> 8);
               }
             }
           } else {
@@ -318,6 +320,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
             for (int i = 0; i < 32; i += 2) {
               const float y0 = kActScale * lrelu(fmaf(__uint_as_float(r[i]), oscale, bias));
               const float y1 = kActScale * lrelu(fmaf(__uint_as_float(r[i + 1]), oscale, bias));
+              amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
               __half2 h, l;
               split2_f16(y0, y1, h, l);
               if (store && p0 + i < kTok) {
@@ -338,6 +341,7 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (!kWvMode) flag_act_overflow(p.status, amax, p.out_fp8 ? kHi8Limit : kF16Limit, p.out_fp8 ? 2 : 3);
     if (p.dbg && warp == 4 && lane == 0) {   // (group 0's view)
       long long* d = p.dbg + blockIdx.x * 8;
       d[5] = clock64() - t_begin; d[6] = w_full_c;

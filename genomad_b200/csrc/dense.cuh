@@ -105,6 +105,30 @@ splitk_reduce_kernel(const float* __restrict__ partials, float* __restrict__ C, 
   C[i] = v;
 }
 
+// Dense epilogue after the tensor-core GEMM (logits_tc_kernel): C[m][n] = epi(sum of the split-K partials in fixed order),
+// epi: v += bias[n]; v = v * scale[n] + shift[n] (Keras BatchNormalization, inference form); relu.  Also writes the value's
+// two TF32 halves (low 13 mantissa bits clear) when the result is the A operand of the next tensor-core GEMM.
+__global__ void __launch_bounds__(256)
+splitk_reduce_epi_kernel(const float* __restrict__ partials, float* __restrict__ C, float* __restrict__ C_hi, float* __restrict__ C_lo,
+                         int M, int N, int parts, const float* __restrict__ bias, const float* __restrict__ scale,
+                         const float* __restrict__ shift, int relu) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(M) * N;
+  if (i >= total) return;
+  const int n = static_cast<int>(i % N);
+  float v = partials[i];
+  for (int z = 1; z < parts; ++z) v += partials[static_cast<size_t>(z) * total + i];
+  v += bias[n];
+  v = v * scale[n] + shift[n];
+  if (relu) v = fmaxf(v, 0.f);
+  C[i] = v;
+  if (C_hi) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    C_hi[i] = hi;
+    C_lo[i] = __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u);
+  }
+}
+
 // Dense(512 -> 3) + softmax: one warp per window.
 __global__ void __launch_bounds__(256)
 dense3_softmax_kernel(const float* __restrict__ h2,    // [n][512]

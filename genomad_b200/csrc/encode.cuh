@@ -95,7 +95,7 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
                    const float* __restrict__ triple,  // [2][4096][128]: A-table, B-table
                    const float* __restrict__ bias,    // [128]
                    uint8_t* __restrict__ y_out,       // [n][5997][768 B] activation rows (hi16 | lo16 | lo8 | hi8)
-                   int n_windows) {
+                   int n_windows, DeviceStatus* status, int experiment) {
   __shared__ int16_t s_tok[kEmbSeg + 8];    // s_tok[i] = token at position t0 - 5 + i, or -1 (causal pad)
   __shared__ uint8_t s_b[kEmbSeg + 16];
   const int w = blockIdx.y;
@@ -154,6 +154,7 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
     // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
     a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
     a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
+    flag_act_overflow(status, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), kHi8Limit, 1);
     __half2 h01, h23, l01, l23;
     split2_f16(a.x, a.y, h01, l01);
     split2_f16(a.z, a.w, h23, l23);
@@ -167,7 +168,8 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
     *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
         static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, (a.y - f1) * kLo8Scale)) |
         (static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, (a.w - f3) * kLo8Scale)) << 16);
-    *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
+    if (!(experiment & 16))                 // timing experiment only: 16 = do not store the hi8 plane (results become wrong)
+      *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
         static_cast<uint32_t>(pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale)) |
         (static_cast<uint32_t>(pack_e4m3x2(f2 * kHi8Scale, f3 * kHi8Scale)) << 16);
   }

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ logits,   // [n][752]
                  const float* __restrict__ q,        // [n][749][128]
                  float* __restrict__ h0,             // [n][256]
+                 float* __restrict__ h0_hi, float* __restrict__ h0_lo,   // TF32 halves of h0 for the tensor-core head (or nullptr)
                  int col_offset) {                   // 0 for IGLOO#0, 128 for IGLOO#1
   __shared__ float s_alpha[kPooled];
   __shared__ float s_red[4];
@@ -179,7 +180,14 @@ attention_kernel(const float* __restrict__ logits,   // [n][752]
     a3 = fmaf(s_alpha[g + 3] * inv, qw[static_cast<size_t>(g + 3) * kC], a3);
   }
   for (; g < kPooled; ++g) a0 = fmaf(s_alpha[g] * inv, qw[static_cast<size_t>(g) * kC], a0);
-  h0[static_cast<size_t>(w) * 256 + col_offset + tid] = (a0 + a1) + (a2 + a3);
+  const float v = (a0 + a1) + (a2 + a3);
+  const size_t o = static_cast<size_t>(w) * 256 + col_offset + tid;
+  h0[o] = v;
+  if (h0_hi) {
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    h0_hi[o] = hi;
+    h0_lo[o] = __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u);
+  }
 }
 
 }  // namespace gnm

@@ -1,4 +1,6 @@
-// K5 on the tensor cores: attention logits = mpi @ w_qk  (reference genomad/neural_network/igloo.py:211), [n x 2100] x [2100 x 749].
+// K5 on the tensor cores: attention logits = mpi @ w_qk  (reference genomad/neural_network/igloo.py:211), [n x 2100] x [2100 x 749],
+// and (round 2) the two Dense(512) projections of the head (reference genomad/neural_network/model.py:28, 40): the same
+// kernel with K = 256 / 512 and N = 512; bias + BatchNorm + ReLU are applied by splitk_reduce_epi_kernel (dense.cuh).
 //
 // fp32 semantics on tcgen05: both operands are split into two TF32 halves, x = hi + lo with hi = x with the low 13 mantissa
 // bits cleared and lo = (x - hi) likewise truncated (so the hardware's fp32 -> tf32 conversion has nothing left to round), and
@@ -28,10 +30,12 @@ constexpr int kLgSmem = kLgStages * kLgStageBytes + 1024 + 256;
 constexpr int kLgThreads = 192;                                   // TMA warp, MMA warp, 4 epilogue warps
 
 struct LogitsTcParams {
-  float* part;               // [kLgSplits][n_rows][ldc]
-  int ldc;                   // 752
+  float* part;               // [gridDim.z splits][n_rows][ldc]
+  int ldc;                   // 752 (logits) / 512 (dense)
   int n_rows;                // windows in this step
-  int n_cols;                // 749
+  int n_cols;                // 749 / 512
+  int chunks_total;          // K chunks of 32 fp32 (the last one may be partly out of bounds -> zero filled by TMA)
+  int chunks_per_split;      // gridDim.z * chunks_per_split >= chunks_total, every split owns >= 1 chunk
   DeviceStatus* status;
 };
 
@@ -72,7 +76,8 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kLgBN, m0 = blockIdx.y * kLgBM, z = blockIdx.z;
-  const int c0 = z * kLgChunksPerSplit;
+  const int c0 = z * p.chunks_per_split;
+  const int nc = min(p.chunks_per_split, p.chunks_total - c0);     // >= 1 by construction of the grid
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
@@ -92,7 +97,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     // ===================================================================== TMA producer
     const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();     // w_qk is re-read by every M tile
-    for (int c = 0; c < kLgChunksPerSplit; ++c) {
+    for (int c = 0; c < nc; ++c) {
       const int s = c % kLgStages;
       const uint32_t ph = (c / kLgStages) & 1;
       mbar_wait(&empty[s], ph ^ 1, p.status, 500 + s);
@@ -108,7 +113,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // ===================================================================== MMA issuer
     const uint64_t desc0 = umma_desc_sw128(0);
     const uint32_t base = smem_u32(smem);
-    for (int c = 0; c < kLgChunksPerSplit; ++c) {
+    for (int c = 0; c < nc; ++c) {
       const int s = c % kLgStages;
       const uint32_t ph = (c / kLgStages) & 1;
       mbar_wait(&full[s], ph, p.status, 510 + s);
@@ -124,7 +129,7 @@ logits_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           umma_tf32(tmem_base, a_hi + kk * 2, b_lo + kk * 2, kIdesc, 1u);
         }
         umma_commit(&empty[s]);
-        if (c == kLgChunksPerSplit - 1) umma_commit(acc_full);
+        if (c == nc - 1) umma_commit(acc_full);
       }
       __syncwarp();
     }

@@ -62,6 +62,7 @@ EXPORTS = {
     "gnm_segment_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gnm_segment_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gnm_classify_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnm_check_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gnm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "gnm_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]),
     "gnm_kernel_launches": (C.c_longlong, [C.c_void_p]),
@@ -236,6 +237,11 @@ class Classifier:
         """Raw-pointer variant (pinned torch tensors): no numpy conversion on the timed path."""
         with self._torch.cuda.device(self.device):
             _check(self.lib, self.lib.gnm_classify_host(self._h, ascii_ptr, n, out_ptr))
+
+    def check_status(self):
+        """Synchronise the current stream and raise GnmError if a step reported a device-side failure
+        (mbarrier time-out, activation range overflow -- see gnm_check_status in include/gnm.h)."""
+        _check(self.lib, self.lib.gnm_check_status(self._h, self._stream()))
 
     # ------------------------------------------------------------------ introspection
     def stage_times(self) -> List[Tuple[str, float]]:

@@ -118,6 +118,15 @@ int gnm_segment_sum(gnm_handle* h, const float* d_probs, const int32_t* d_offset
                     float* d_sum4, void* stream);
 
 /*
+ * Synchronise `stream` and report device-side failures of the steps queued so far: an mbarrier time-out (protocol bug),
+ * or an ACTIVATION RANGE OVERFLOW -- the tensor-core convs carry activations as fp16 + e4m3 correction planes scaled for
+ * |y| <= 3.5 (csrc/common.cuh); weights that drive a layer-1 or conv output beyond that (fp16: 2047) would silently lose the
+ * 1e-4 parity, so the producing kernels raise a flag and the library fails loudly instead.  gnm_forward_* are asynchronous
+ * and only see the flag at the start of the NEXT call; gnm_classify_host checks before it returns.
+ */
+int gnm_check_status(gnm_handle* h, void* stream);
+
+/*
  * Host-buffer convenience path (what a drop-in module calls): h_ascii uint8 [n][6000] in host
  * memory (pinned or pageable) -> h_probs float [n][3].  Copies in steps of max_batch on two
  * internal streams so the copy of step i+1 overlaps the compute of step i.  Synchronous.
@@ -178,7 +187,7 @@ uint32_t gnm_crc32c(const void* data, size_t n);
  * "debug_stop" 0 = full pipeline, 1 = stop after layer 1 + gather#0, 2 = after conv2, 3 = after conv3;
  * "profile_stages" 1 = record a CUDA event between stages (see gnm_stage_times);
  * "conv_experiment" bit mask for timing experiments on the conv kernel: 2 = skip the epilogue's global stores (results
- * become wrong), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg");
+ * become wrong), 16 = layer 1 and conv2 do not store the derivable hi8 plane (upper bound of what dropping it from HBM could save), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg");
  * "fuse_l1" 1 = run layer 1 and the first IGLOO kernel's value projection as ONE kernel (csrc/layer1_wv.cuh: SIMT producers
  * write the tensor core's B operand straight into swizzled shared memory; bit-identical results, 17 instead of 18 launches
  * per step; measured slower than the two separate kernels at the end of round 1, hence 0 by default). */

@@ -9,7 +9,7 @@ Nothing under ``genomad_b200/`` imports it.
 
 What is pinned and what is not
 ------------------------------
-* Tokenizer / windowing / FASTA reader (``oracle/tokenizer.py``, ``oracle/c/gnm_oracle.c``):
+* Tokenizer / windowing / FASTA reader (``oracle/tokenizer.py``; pure NumPy, there is no C restatement):
   PINNED.  They are checked against golden vectors produced by running the *real*
   reference code (``/root/reference/genomad/sequence.py`` under numba) in the build
   container; generator: ``tests/golden/make_golden.py``, vectors: ``tests/golden/*.npz|json``.

@@ -18,4 +18,5 @@ def test_two_gpu_parity(repo_root):
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(repo_root / "tools" / "multigpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "gather bitwise-equal: True" in r.stdout and "module driver under torchrun" in r.stdout
+    assert "gather bitwise-equal: True" in r.stdout and "module driver under torchrun x2 (gather): NPZ equals" in r.stdout
+    assert "(allreduce): max |d|" in r.stdout

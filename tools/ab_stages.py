@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""
+Same-box A/B of library options: per-stage CUDA-event times and whole-step time at batch 1024 (device-resident windows).
+
+    python tools/ab_stages.py fuse_gather=1 fuse_gather=0 [--batch 1024] [--steps 30] [--check]
+
+Every positional argument is one configuration: comma-separated option=value pairs applied with gnm_set_option.
+--check compares the probabilities of every configuration with the first one (max |dp|).
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from genomad_b200 import engine, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["fuse_gather=1", "fuse_gather=0"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    B = args.batch
+    clf = engine.Classifier(None, device=0, max_batch=B)
+    pool = [synth.windows_torch(1000 * i, B, 1, "cuda") for i in range(3)]
+    out = torch.empty((B, 3), dtype=torch.float32, device="cuda")
+    base = None
+    for rep in range(2):                                       # two rounds: the second is at the settled clock
+        for cfg in args.configs:
+            for k in ("conv_experiment",):                       # options not named in a configuration are back at their defaults
+                clf.set_option(k, 0)
+            clf.set_option("fuse_gather", 1)
+            for kv in cfg.split(","):
+                k, v = kv.split("=")
+                clf.set_option(k, int(v))
+            for i in range(3):
+                clf.predict_ascii(pool[i % 3], out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                clf.predict_ascii(pool[i % 3], out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            clf.set_option("profile_stages", 1)
+            for i in range(6):
+                clf.predict_ascii(pool[i % 3], out)
+            torch.cuda.synchronize()
+            acc = {}
+            for name, t in clf.stage_times():
+                acc.setdefault(name, []).append(t)
+            clf.set_option("profile_stages", 0)
+            clf.check_status()
+            line = "  ".join(f"{k}={sum(v) / len(v):.3f}" for k, v in acc.items())
+            print(f"[round {rep}] {cfg}: {ms:.3f} ms/step = {B / ms * 1e3:,.0f} windows/s | {line}", flush=True)
+            if args.check and rep == 0:
+                pr = clf.predict_ascii(pool[0]).clone()
+                if base is None:
+                    base = pr
+                else:
+                    print(f"    max |dp| vs first configuration: {(pr - base).abs().max().item():.2e}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
