@@ -103,12 +103,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  // The fourth operand is the suspend-time hint (ns): the waiting thread is parked in hardware until the phase completes or
+  // the hint expires.  Without it a waiter wakes every few hundred cycles and re-issues the whole spin loop -- ncu on the
+  // fused IGLOO kernel counted ~60 try_waits per warp and unit, i.e. a fifth of all issued instructions in a kernel
+  // whose consumer warps are short of issue slots.
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must become a CUDA error, never a hung GPU box.

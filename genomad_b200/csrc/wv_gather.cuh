@@ -34,8 +34,8 @@
 //     to global loads): ncu on the first version showed the warps stalled on exactly those global loads.  patch_finish_t_kernel adds a patch's four slots in
 //     fixed order k = 0..3 plus the bias, as before.
 //
-// Warp roles (640 threads, 1 CTA per SM):  warp 0 lane 0: weight loader (once) | warp 1: tcgen05.mma issuer |
-// warp 2: TMEM allocator | warp 3 lane 0: activation producer (TMA) | warps 4..19: patch gather, then epilogue
+// Warp roles (768 threads, 1 CTA per SM):  warp 0 lane 0: weight loader (once) | warp 1: tcgen05.mma issuer |
+// warp 2: TMEM allocator | warp 3 lane 0: activation producer (TMA) | warps 4..23: patch gather, then epilogue
 // (max over 8 positions = max over 8 registers; a warp writes 128 contiguous bytes of q[g][:] per pooled row).
 #pragma once
 #include <cuda.h>
@@ -50,11 +50,15 @@ constexpr int kBandRows   = 32;                                   // positions p
 constexpr int kBandWins   = 8;                                    // windows per unit
 constexpr int kNumBands   = (kTok + kBandRows - 1) / kBandRows;   // 188 (the last band holds 13 valid rows)
 constexpr int kWgRegion   = kBandRows * kBandWins * 128;          // bytes per slab region (256 rows x 128 B) = 32768
-constexpr int kWgSlab     = 4 * kWgRegion;                        // hi16.k0 | hi16.k1 | lo16.k0 | lo16.k1       = 131072
+constexpr int kWgBufs     = 4;                                    // region buffers.  The code is a ring (region k of unit `it` lives in buffer
+                                                                  // (4 it + k) % kWgBufs): with 5 buffers the TMA can run one region ahead of
+                                                                  // the consumers' releases -- measured, no gain (1.15 / 1.26 ms vs 1.05 / 1.14),
+                                                                  // so the slab stays at exactly one unit
+constexpr int kWgSlab     = kWgBufs * kWgRegion;                  // hi16.k0 | lo16.k0 | hi16.k1 | lo16.k1        = 131072
 constexpr int kWgWeights  = kWvStages * kBStage;                  // resident w_v stages                         =  65536
-constexpr int kWgWarps    = 16;                                   // consumer warps: patch gather + accumulator epilogue
-constexpr int kWgThreads  = (4 + kWgWarps) * 32;                  // 640
-constexpr int kWgWarpCap  = 4;                                    // entries per warp on the fast path (64 per band; mean 45)
+constexpr int kWgWarps    = 20;                                   // consumer warps: patch gather + accumulator epilogue
+constexpr int kWgThreads  = (4 + kWgWarps) * 32;                  // 768
+constexpr int kWgWarpCap  = 3;                                    // entries per warp on the fast path (60 per band; mean 45)
 constexpr int kWgSmem     = kWgSlab + kWgWeights + 2048;          //                                                   = 198656
 static_assert(kWgSmem <= 232448, "wv_gather_kernel exceeds the 227 KB of shared memory a CTA may use");
 static_assert(kBandRows * kBandWins == 256, "one unit = one N = 256 tile");
@@ -69,6 +73,7 @@ struct WvGatherParams {
   int n_windows, n_pad;        // n_pad = n rounded up to a multiple of 8
   int groups;                  // window groups per band = n_pad / 8
   int n_units;                 // kNumBands * groups
+  const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
   int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores
   DeviceStatus* status;
 };
@@ -100,25 +105,27 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
   constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_a = smem;                                   // 4 regions x [8 windows][32 rows] x 128 B
+  uint8_t* s_a = smem;                                   // ring of kWgBufs region buffers, each [8 windows][32 rows] x 128 B
   uint8_t* s_w = smem + kWgSlab;                         // 4 resident weight stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kWgWeights);
-  uint64_t* a_full = bars;            // [4]  per region
-  uint64_t* a_empty = bars + 4;       // [4]
-  uint64_t* w_full = bars + 8;        // [1]
-  uint64_t* acc_full = bars + 9;      // [2]
-  uint64_t* acc_empty = bars + 11;    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* a_full = bars;            // [kWgBufs <= 5]  per buffer
+  uint64_t* a_empty = bars + 5;       // [kWgBufs <= 5]
+  uint64_t* w_full = bars + 10;       // [1]
+  uint64_t* acc_full = bars + 11;     // [2]
+  uint64_t* acc_empty = bars + 13;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 15);
+  // Region k of a unit (need order: 0 hi16.k0, 1 lo16.k0, 2 hi16.k1, 3 lo16.k1) is load number g = 4 * it + k of this CTA and
+  // lives in buffer g % kWgBufs; every role walks the buffers in the same order, so each keeps the first buffer of the
+  // current unit (b0, advanced by 4 mod kWgBufs per unit) and one phase bit per buffer that it flips after each use.
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // contiguous, balanced range of band-major unit numbers
-  const int u_begin = static_cast<int>(static_cast<long long>(p.n_units) * blockIdx.x / gridDim.x);
-  const int u_end = static_cast<int>(static_cast<long long>(p.n_units) * (blockIdx.x + 1) / gridDim.x);
+  // contiguous range of band-major unit numbers; the split points weigh a unit by its band's entry count (host side)
+  const int u_begin = p.cta_split[blockIdx.x], u_end = p.cta_split[blockIdx.x + 1];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_band);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the consumer warps
+    for (int i = 0; i < kWgBufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the consumer warps
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kWgWarps); }
     fence_barrier_init();
@@ -140,18 +147,22 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
   } else if (warp == 3 && lane == 0) {
     // ===================================================================== activation producer
     const uint64_t pol = l2_policy_evict_first();
-    int it = 0;
-    for (int unit = u_begin; unit < u_end; ++unit, ++it) {
-      const uint32_t ph = it & 1;
+    uint32_t phases = 0;                                   // bit b: parity of buffer b's next "empty" wait is phase ^ 1
+    int b0 = 0;
+    for (int unit = u_begin; unit < u_end; ++unit) {
       const int band = unit / p.groups;
       const int w0 = (unit - band * p.groups) * kBandWins;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int r = k == 0 ? 0 : k == 1 ? 2 : k == 2 ? 1 : 3;                  // order in which the MMAs need them
-        mbar_wait(&a_empty[r], ph ^ 1, p.status, 500 + r);
-        mbar_arrive_expect_tx(&a_full[r], kWgRegion);
-        tma_load_3d_hint(s_a + r * kWgRegion, &tm_band, &a_full[r], region_src<true>(r), band * kBandRows, w0, pol);
+        int b = b0 + k; if (b >= kWgBufs) b -= kWgBufs;
+        mbar_wait(&a_empty[b], ((phases >> b) & 1) ^ 1, p.status, 500 + b);
+        phases ^= 1u << b;
+        mbar_arrive_expect_tx(&a_full[b], kWgRegion);
+        // k: 0 hi16 channels 0-63, 1 lo16 channels 0-63, 2 hi16 channels 64-127, 3 lo16 channels 64-127 (byte offset in the row)
+        const int src = (k & 1 ? kOffLo16 : kOffHi16) + (k >> 1) * 128;
+        tma_load_3d_hint(s_a + b * kWgRegion, &tm_band, &a_full[b], src, band * kBandRows, w0, pol);
       }
+      b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (converged warp, elected lane issues)
@@ -160,44 +171,48 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     const uint32_t w_base = smem_u32(s_w);
     mbar_wait(w_full, 0, p.status, 510);
     int it = 0;
+    uint32_t phases = 0;
+    int b0 = 0;
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
-      const uint32_t aph = it & 1;
       const uint32_t acc = tmem_base + as * 256;
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 520 + as);
 #pragma unroll
       for (int q = 0; q < kWvStages; ++q) {
         // stage q = (K-half q/2, weight hi/lo q%2); hi-weight stages multiply both the hi16 and the lo16 region
-        const int reg = q >> 1;
+        const int kh = q >> 1;
+        int bh = b0 + 2 * kh; if (bh >= kWgBufs) bh -= kWgBufs;               // hi16 region of this K-half
+        int bl = b0 + 2 * kh + 1; if (bl >= kWgBufs) bl -= kWgBufs;           // lo16 region
         if ((q & 1) == 0) {
-          mbar_wait(&a_full[reg], aph, p.status, 530 + reg);
-          mbar_wait(&a_full[2 + reg], aph, p.status, 534 + reg);
+          mbar_wait(&a_full[bh], (phases >> bh) & 1, p.status, 530 + bh);
+          mbar_wait(&a_full[bl], (phases >> bl) & 1, p.status, 536 + bl);
+          phases ^= (1u << bh) | (1u << bl);
         }
         tc_fence_after();
         if (elect_one()) {
           const uint64_t wdesc = desc0 + ((w_base + q * kBStage) >> 4);                      // A: weights
-          const uint64_t y0 = desc0 + ((a_base + reg * kWgRegion) >> 4);                     // B: hi16 rows
-          const uint64_t y1 = desc0 + ((a_base + (2 + reg) * kWgRegion) >> 4);               // B: lo16 rows
+          const uint64_t y0 = desc0 + ((a_base + bh * kWgRegion) >> 4);                      // B: hi16 rows
+          const uint64_t y1 = desc0 + ((a_base + bl * kWgRegion) >> 4);                      // B: lo16 rows
           const bool w_lo = (q & 1) != 0;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
             if (!w_lo) umma_f16(acc, wdesc + kk * 2, y1 + kk * 2, kIdesc, 1u);
           }
-          if (q == 0) umma_commit(&a_empty[2]);                  // lo16.k0 is only used by stage 0
-          if (q == 1) umma_commit(&a_empty[0]);
-          if (q == 2) umma_commit(&a_empty[3]);
-          if (q == 3) { umma_commit(&a_empty[1]); umma_commit(&acc_full[as]); }
+          if (!w_lo) umma_commit(&a_empty[bl]);                  // the lo16 region is only used by the hi-weight stage
+          else umma_commit(&a_empty[bh]);
+          if (q == 3) umma_commit(&acc_full[as]);
         }
         __syncwarp();
       }
+      b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }
   } else if (warp >= 4) {
     // ===================================================================== patch gather, then accumulator epilogue
-    const int gw = warp - 4;                                   // 0..15
+    const int gw = warp - 4;                                   // 0..19
     const int wq = warp & 3;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
-    const int grp = gw >> 2;                                   // epilogue: windows grp and grp+4 of the unit
+    const int grp = gw >> 2;                                   // epilogue: windows grp and grp+5 of the unit
     const int ch = wq * 32 + lane;
     const float oscale = p.out_scale;
     // gather lane roles: quarter-warp (lane >> 3): 0 = hi row of the even window, 1 = lo row of the even window,
@@ -220,13 +235,14 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       return c;
     };
     int it = 0;
+    uint32_t phases = 0;
+    int b0 = 0;
     int cur_band = -1, e_begin = 0, cnt = 0;
-    int rr[kWgWarpCap] = {0, 0, 0, 0};                         // rows (inside the band) of this warp's entries, fast path
+    int rr[kWgWarpCap] = {0, 0, 0};                         // rows (inside the band) of this warp's entries, fast path
     bool fast = true;
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int band = unit / p.groups;
       const int w0 = (unit - band * p.groups) * kBandWins;
-      const uint32_t aph = it & 1;
       if (band != cur_band) {                                  // this warp's contiguous run of the band's entries
         cur_band = band;
         const int b0 = p.band_start[band], b1 = p.band_start[band + 1];
@@ -244,7 +260,11 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       float c0[kWgWarpCap];                                    // pass-0 halves of the fast path (lanes with (lane & 3) == 0)
 #pragma unroll 1
       for (int kh = 0; kh < 2; ++kh) {
-        const uint32_t reg_base = slab + (plane ? 2 + kh : kh) * kWgRegion + wodd * (kBandRows * 128) + (jch << 4);
+        int bh = b0 + 2 * kh; if (bh >= kWgBufs) bh -= kWgBufs;               // buffer of this K-half's hi16 region
+        int bl = b0 + 2 * kh + 1; if (bl >= kWgBufs) bl -= kWgBufs;           // ... and of its lo16 region
+        const uint32_t ph_h = (phases >> bh) & 1, ph_l = (phases >> bl) & 1;
+        phases ^= (1u << bh) | (1u << bl);
+        const uint32_t reg_base = slab + (plane ? bl : bh) * kWgRegion + wodd * (kBandRows * 128) + (jch << 4);
         if (fast) {
           // the folded weights do not depend on the slab: request them (L1 / L2) BEFORE waiting for the TMA data
           float4 wa[kWgWarpCap], wb[kWgWarpCap];
@@ -254,8 +274,8 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
               const float* wp = p.ent_w + static_cast<size_t>(e_begin + i) * kC + kh * 64 + jch * 8;
               wa[i] = ldg_weights(wp); wb[i] = ldg_weights(wp + 4);
             }
-          mbar_wait(&a_full[kh], aph, p.status, 550 + kh);            // hi16 K-half kh
-          mbar_wait(&a_full[2 + kh], aph, p.status, 552 + kh);        // lo16 K-half kh
+          mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);          // hi16 K-half kh
+          mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);          // lo16 K-half kh
 #pragma unroll
           for (int i = 0; i < kWgWarpCap; ++i)
             if (i < cnt) {
@@ -269,8 +289,8 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
             }
         } else {
           // generic path (band with more than 64 entries): pass-0 halves parked in part_t itself
-          mbar_wait(&a_full[kh], aph, p.status, 550 + kh);
-          mbar_wait(&a_full[2 + kh], aph, p.status, 552 + kh);
+          mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);
+          mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);
 #pragma unroll 1
           for (int i = 0; i < cnt; ++i) {
             const int e = e_begin + i;
@@ -289,8 +309,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
           }
         }
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&a_empty[kh]); mbar_arrive(&a_empty[2 + kh]); }       // this warp is done with the K-half's regions
+        if (lane == 0) { mbar_arrive(&a_empty[bh]); mbar_arrive(&a_empty[bl]); }           // this warp is done with the K-half's regions
       }
+      b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
       // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;

@@ -27,6 +27,9 @@ from ._paths import NNOutputs
 
 _HEADER = "seq_name\tchromosome_score\tplasmid_score\tvirus_score\n"
 
+# wall-clock breakdown of the most recent main() call on this rank (seconds): read by bench.py's module_e2e report
+last_timings: dict = {}
+
 
 DEVICE_STEP_MIN, DEVICE_STEP_MAX = 1024, 4096
 _WORKSPACE_BYTES_PER_WINDOW = 7.0e6          # libgnm workspace per window of max_batch
@@ -42,12 +45,31 @@ def device_step(batch_size: int, free_bytes: int) -> int:
     return step
 
 
+_CLASSIFIERS: dict = {}          # (device, windows per step) -> engine.Classifier, kept for the life of the process
+
+
+def release_classifiers() -> None:
+    """Destroy the cached classifiers (frees ~7 GB of HBM per device; the next main() call rebuilds them)."""
+    for c in list(_CLASSIFIERS.values()):
+        c.close()
+    _CLASSIFIERS.clear()
+
+
 def _make_classifier(batch_size: int, device: int):
-    """Factory (patched in CPU tests): the real one needs a B200 and libgnm.so -- no fallback."""
+    """Factory (patched in CPU tests): the real one needs a B200 and libgnm.so -- no fallback.
+    The classifier (weights re-packed on the device + workspace, ~0.3 s to build and ~0.4 s to free) stays resident between
+    main() calls of one process -- `genomad end-to-end`, a service, the provirus twin -- unless GENOMAD_B200_KEEP_MODEL=0."""
     import torch
     from .engine import Classifier
     free, _total = torch.cuda.mem_get_info(device)
-    return Classifier(None, device=device, max_batch=device_step(batch_size, free))
+    keep = os.environ.get("GENOMAD_B200_KEEP_MODEL", "1") not in ("", "0")
+    for (dev, step), c in _CLASSIFIERS.items():
+        if dev == device and keep:
+            return c                                          # its step already fitted this device
+    clf = Classifier(None, device=device, max_batch=device_step(batch_size, free))
+    if keep:
+        _CLASSIFIERS[(device, clf.max_batch)] = clf
+    return clf
 
 
 def _pinned_chunk(n: int):
@@ -183,6 +205,9 @@ def contig_reduce_mode(default: str = "gather") -> str:
 
 
 def main(input_path, output_path, single_window, batch_size, restart, threads, verbose, cleanup, *, contig_reduce=None):
+    import time as _time
+    t_start = _time.perf_counter()
+    last_timings.clear()
     input_path, output_path = Path(input_path), Path(output_path)
     info = gdist.init_process_group_if_needed()
     is_main = info.is_main
@@ -217,6 +242,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                          "nucleotide sequence.", outputs.nn_classification_dir, files, descr)
 
     parsed_input = sequence.ParsedFasta(input_path, single_window, threads)      # one native index pass: check + windows
+    last_timings["index_s"] = _time.perf_counter() - t_start
     if not parsed_input.check():
         console.error(f"{input_path} is either empty or contains multiple entries with the same identifier. "
                       "Please check your input FASTA file and execute genomad nn-classification again.")
@@ -231,6 +257,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
                      outputs.provirus_nn_classification_npz_output, outputs.provirus_nn_classification_output, False))
 
     plan = None
+    info_writer = None
     if is_main:
         skip = False
         if outputs.nn_classification_execution_info.exists() and any(p.exists() for p in files) and not restart:
@@ -246,8 +273,14 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             outputs.nn_classification_dir.mkdir()
         # per job: (skip the encoding stage, skip the classification) -- decided BEFORE anything is rewritten
         plan = [(bool(skip and j[4].exists()), bool(skip and j[7].exists())) for j in jobs]
-        utils.write_execution_info("nn_classification", input_path, parameter_dict,
-                                   outputs.nn_classification_execution_info)
+        # The execution info carries the input's md5 (aggregated-classification cross-checks it).  md5 is sequential
+        # (~0.6 GB/s): writing the JSON here, as the reference does, would hold the GPUs back until the whole file is hashed,
+        # so it is written by a helper thread as soon as the background hash is done and joined before main() returns.
+        import threading
+        info_writer = threading.Thread(target=utils.write_execution_info, daemon=True,
+                                       args=("nn_classification", input_path, parameter_dict,
+                                             outputs.nn_classification_execution_info))
+        info_writer.start()
     plan = gdist.broadcast_object(plan, info)
 
     # the classifier (CUDA context, weight upload, TMA descriptors: ~0.3 s) is built on a helper thread while the host
@@ -288,10 +321,14 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             if parsed.n_windows == 0:
                 if must_have_windows:
                     console.error("No sequences were found. Please check your input FASTA.")
+                    if info_writer is not None:
+                        info_writer.join()                    # the reference has written the JSON by this point
                     sys.exit(1)
                 names, preds = index.names, np.zeros((len(index.names), 3), np.float32)
             else:
+                t_c = _time.perf_counter()
                 preds = _classify_parsed(classifier(), parsed, index.offsets, info, contig_reduce)
+                last_timings[f"classify_{what}_s"] = _time.perf_counter() - t_c          # incl. waiting for the CUDA context
                 names = index.names
             console.log(f"{'Sequences' if what == 'sequence' else 'Proviruses'} classified.")
             if is_main:
@@ -307,5 +344,10 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
         console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
 
     clf_pool.shutdown(wait=True)
-    gdist.barrier(info)                                   # rank 0 has written everything before any rank returns
+    t_j = _time.perf_counter()
+    if info_writer is not None:
+        info_writer.join()
+    last_timings["wait_for_md5_json_s"] = _time.perf_counter() - t_j
+    gdist.barrier(info)
+    last_timings["total_s"] = _time.perf_counter() - t_start                                   # rank 0 has written everything before any rank returns
     console.log("geNomad nn-classification finished!")

@@ -178,7 +178,7 @@ class ParsedFasta:
         from . import engine
         self._lib = engine.load_library()
         avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        self._threads = max(1, min(int(threads), avail)) if threads else min(32, avail)    # --threads is honoured
+        self._threads = max(1, min(int(threads), avail, 32)) if threads else min(32, avail)    # --threads is honoured (32 saturate the reader)
         self._h = C.c_void_p()
         if is_compressed(path) == Compression.uncompressed:
             self._text = None                               # mmap inside the library: the file is never copied

@@ -35,6 +35,7 @@ def main():
             for k in ("conv_experiment",):                       # options not named in a configuration are back at their defaults
                 clf.set_option(k, 0)
             clf.set_option("fuse_gather", 1)
+            clf.set_option("conv_cluster", 1)
             for kv in cfg.split(","):
                 k, v = kv.split("=")
                 clf.set_option(k, int(v))
