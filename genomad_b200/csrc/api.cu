@@ -185,13 +185,15 @@ static void pack_stage_f16(std::vector<uint8_t>& dst, const float* Wkn /* [128 k
       dst.push_back(static_cast<uint8_t>(bits >> 8));
     }
 }
-// One 16 KB e4m3 TMA stage: B[n][k] = e4m3(part(W[k][n]) * scale), all 128 input channels in one 128-byte row.
-static void pack_stage_f8(std::vector<uint8_t>& dst, const float* Wkn, int w_lo, float scale) {
+// One 16 KB e4m3 TMA stage of the correction passes: B[n][2c + s] for the 64 input channels c of K-half kh, interleaved like the
+// activation pairs (common.cuh): s = 0 multiplies lo8(A) -> e4m3(Whi * scale_hi), s = 1 multiplies hi8(A) -> e4m3(Wlo * scale_lo).
+static void pack_stage_f8_pairs(std::vector<uint8_t>& dst, const float* Wkn, int kh, float scale_hi, float scale_lo) {
   for (int n = 0; n < kC; ++n)
-    for (int k = 0; k < kC; ++k) {
-      const float x = Wkn[static_cast<size_t>(k) * kC + n];
+    for (int c = 0; c < 64; ++c) {
+      const float x = Wkn[static_cast<size_t>(kh * 64 + c) * kC + n];
       const float hi = __half2float(__float2half_rn(x));
-      dst.push_back(static_cast<uint8_t>(__nv_cvt_float_to_fp8((w_lo ? x - hi : hi) * scale, __NV_SATFINITE, __NV_E4M3)));
+      dst.push_back(static_cast<uint8_t>(__nv_cvt_float_to_fp8(hi * scale_hi, __NV_SATFINITE, __NV_E4M3)));
+      dst.push_back(static_cast<uint8_t>(__nv_cvt_float_to_fp8((x - hi) * scale_lo, __NV_SATFINITE, __NV_E4M3)));
     }
 }
 
@@ -252,15 +254,14 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
       const int d = 16 - shift, S = 5 + d;
       if (d < 1) return fail("gnm_create: conv weights too large for the fp16 operand format");
       h->conv_out_scale[L] = std::ldexp(1.f, -S);
-      std::vector<uint8_t> pk;                              // (region, tap): hi16.k0 x6, hi16.k1 x6, lo8 x6, hi8 x6
+      std::vector<uint8_t> pk;                              // (region, tap): hi16.k0 x6, hi16.k1 x6, pairs.k0 x6, pairs.k1 x6
       pk.reserve(static_cast<size_t>(kConvStages) * kBStage);
       for (int kh = 0; kh < 2; ++kh)
         for (int tap = 0; tap < kTaps; ++tap)
           pack_stage_f16(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 0, kh, std::ldexp(1.f, d));
-      for (int tap = 0; tap < kTaps; ++tap)                 // x lo8 = e4m3(Alo * 2^12):  e4m3(Whi * 2^(S-12))
-        pack_stage_f8(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 0, std::ldexp(1.f, S - 12));
-      for (int tap = 0; tap < kTaps; ++tap)                 // x hi8 = e4m3(Ahi * 2^7):   e4m3(Wlo * 2^(S-7))
-        pack_stage_f8(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, 1, std::ldexp(1.f, S - 7));
+      for (int kh = 0; kh < 2; ++kh)                        // x (lo8, hi8) = (e4m3(Alo * 2^12), e4m3(Ahi * 2^7)):  (e4m3(Whi * 2^(S-12)), e4m3(Wlo * 2^(S-7)))
+        for (int tap = 0; tap < kTaps; ++tap)
+          pack_stage_f8_pairs(pk, convw[L] + static_cast<size_t>(tap) * kC * kC, kh, std::ldexp(1.f, S - 12), std::ldexp(1.f, S - 7));
       if (dev_upload(h, &h->wpack[L], pk.data(), pk.size())) return 1;
       if (dev_upload(h, &h->conv_w32[L], convw[L], static_cast<size_t>(kTaps) * kC * kC)) return 1;
     }
@@ -673,9 +674,9 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   } else {
   timer_mark(h, "embed_conv1", st);
   if (d_ascii)
-    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status, h->conv_experiment);
+    embed_conv1_kernel<true><<<egrid, kEmbThreads, 0, st>>>(d_ascii, nullptr, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status);
   else
-    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status, h->conv_experiment);
+    embed_conv1_kernel<false><<<egrid, kEmbThreads, 0, st>>>(nullptr, d_tok, h->conv1_table, h->conv1_triple, h->conv1_bias, h->ybuf[0], n, h->status);
   if (check_launch(h, "embed_conv1_kernel")) return 1;
   }
   const bool fg = h->fuse_gather && h->conv_impl == 0 && !fused;     // w_v + gather in one kernel (wv_gather.cuh)

@@ -28,10 +28,13 @@ constexpr float kLeaky  = 0.1f;   // LeakyReLU slope                   (referenc
 // DeviceStatus::act_overflow (reported by the next API call as an error); the shipped model stays below |y| = 0.7.
 //   [  0,256)  hi16 = fp16(Y)                       128 halves   -- main tensor-core operand, w_v, patch gather
 //   [256,512)  lo16 = fp16(Y - hi16)                128 halves   -- w_v 3-pass split, patch gather
-//   [512,640)  lo8  = e4m3((Y - hi16) * 128)        128 bytes    -- conv correction pass  lo(A) * hi(W)
-//   [640,768)  hi8  = e4m3(hi16 * 4)                128 bytes    -- conv correction pass  hi(A) * lo(W)
+//   [512,768)  p8   = 128 e4m3 PAIRS (lo8[c], hi8[c]),  lo8 = e4m3((Y - hi16) * 128), hi8 = e4m3(hi16 * 4)
+//                     -- the operand of the convs' correction passes lo(A) * hi(W) + hi(A) * lo(W), which run as ONE K = 256
+//                     contraction against weights interleaved the same way (Whi8[c], Wlo8[c]).  Interleaving (round 2) lets a
+//                     producer write a channel's two bytes with one store (conv2's epilogue: one 2-byte store per position
+//                     instead of two 1-byte stores; layer 1: one 8-byte store per lane instead of two 4-byte stores).
 constexpr int kRowBytes  = 768;
-constexpr int kOffHi16   = 0, kOffLo16 = 256, kOffLo8 = 512, kOffHi8 = 640;
+constexpr int kOffHi16   = 0, kOffLo16 = 256, kOffP8 = 512;
 constexpr float kActScale = 32.f;          // 2^5
 constexpr float kLo8Scale = 128.f;         // lo8 = (Y - hi16) * 2^7   -> y_lo * 2^12
 constexpr float kHi8Scale = 4.f;           // hi8 = hi16 * 2^2         -> y_hi * 2^7

@@ -99,7 +99,7 @@ __global__ void join_rows_kernel(const uint8_t* __restrict__ y_in, float* __rest
   const float hi = __half2float(reinterpret_cast<const __half*>(row + kOffHi16)[c]);
   float lo;
   if (fp8_lo) {
-    const __half_raw hr = __nv_cvt_fp8_to_halfraw(row[kOffLo8 + c], __NV_E4M3);
+    const __half_raw hr = __nv_cvt_fp8_to_halfraw(row[kOffP8 + 2 * c], __NV_E4M3);        // pair (lo8[c], hi8[c])
     lo = __half2float(__half(hr)) * (1.f / kLo8Scale);
   } else {
     lo = __half2float(reinterpret_cast<const __half*>(row + kOffLo16)[c]);

@@ -21,9 +21,9 @@
 //         corr2 : e4m3(Ahi * 2^7)     x e4m3(Wlo * 2^(S-7))
 //     CPU emulation of exactly this recipe: max |dp| 6.5e-6 over 256 worst-case-family windows.
 //
-// Data layout.  Activation rows are 768 bytes: hi16 | lo16 | lo8 | hi8 (common.cuh), tensor [n][5997][768 B].
+// Data layout.  Activation rows are 768 bytes: hi16 | lo16 | e4m3 pairs (lo8[c], hi8[c]) (common.cuh), tensor [n][5997][768 B].
 // One work unit = 256 consecutive positions of one window (24 units per window).  The unit's operands
-// are four slab REGIONS of 272 rows x 128 bytes (conv: hi16 ch 0-63, hi16 ch 64-127, lo8, hi8;
+// are four slab REGIONS of 272 rows x 128 bytes (conv: hi16 ch 0-63, hi16 ch 64-127, e4m3 pairs of ch 0-63, of ch 64-127;
 // w_v: hi16 and lo16 halves); two TMA boxes of 136 rows bring rows t0-5 .. t0+266 of the window into
 // each SWIZZLE_128B region ONCE; conv tap j is the same slab read j rows further down -- only the
 // UMMA descriptor start address changes (row j is position t0-5+j; TMA zero-fills rows with t < 0 or
@@ -89,7 +89,7 @@ struct ConvTcParams {
   float out_scale;          // conv: 2^-S (undoes the common operand scaling); w_v: 1/32 (activation scale)
   int out_fp8;              // conv: 1 = write hi16 + lo8 + hi8 (consumer is a conv), 0 = write hi16 + lo16
   int n_tiles;              // number of work units = n_windows * 24
-  int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores, 16 = no hi8-plane stores
+  int experiment;           // timing experiments only (results become wrong): 2 = no epilogue global stores
   long long* dbg;           // optional [gridDim.x][8] cycle counters (nullptr = off)
   DeviceStatus* status;
 };
@@ -97,7 +97,7 @@ struct ConvTcParams {
 // byte offset inside the 768-byte activation row of the data that fills slab region r
 template <bool kWvMode> __device__ __forceinline__ constexpr int region_src(int r) {
   return kWvMode ? (r == 0 ? kOffHi16 : r == 1 ? kOffHi16 + 128 : r == 2 ? kOffLo16 : kOffLo16 + 128)
-                 : (r == 0 ? kOffHi16 : r == 1 ? kOffHi16 + 128 : r == 2 ? kOffLo8 : kOffHi8);
+                 : (r == 0 ? kOffHi16 : r == 1 ? kOffHi16 + 128 : r == 2 ? kOffP8 : kOffP8 + 128);
 }
 
 template <bool kWvMode>
@@ -194,7 +194,8 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 200 + as);
       w_acc += clock64() - tq;
       for (int q = 0; q < kStagesU; ++q, ++wcount) {
-        // conv: stage q = (region q/6, tap q%6); regions 0,1 are fp16 K-halves, 2 = lo8 (x Whi8), 3 = hi8 (x Wlo8)
+        // conv: stage q = (region q/6, tap q%6); regions 0,1 are fp16 K-halves, 2 / 3 = e4m3 pairs (lo8, hi8) of channels 0-63 / 64-127
+        //       against weights interleaved the same way (Whi8, Wlo8)
         // w_v : stage q = (K-half q/2, weight hi/lo q%2); hi-weight stages multiply both the hi16 and the lo16 region
         const int reg = kWvMode ? (q >> 1) : (q / 6);
         const int tap = kWvMode ? 5 : (q - reg * 6);
@@ -300,19 +301,18 @@ conv_t_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant_
               amax = fmaxf(amax, fmaxf(fabsf(y0), fabsf(y1)));
               const __half2 h = __floats2half2_rn(y0, y1);
               const float2 f = __half22float2(h);
-              const uint16_t lo = pack_e4m3x2((y0 - f.x) * kLo8Scale, (y1 - f.y) * kLo8Scale);
-              const uint16_t hi = pack_e4m3x2(f.x * kHi8Scale, f.y * kHi8Scale);
+              // e4m3 pair (lo8, hi8) of this channel at each of the two positions: one 2-byte store per position
+              const uint16_t e0 = pack_e4m3x2((y0 - f.x) * kLo8Scale, f.x * kHi8Scale);
+              const uint16_t e1 = pack_e4m3x2((y1 - f.y) * kLo8Scale, f.y * kHi8Scale);
               if (store && p0 + i < kTok) {
                 uint8_t* q = rowp + i * kRowBytes;
                 reinterpret_cast<__half*>(q + kOffHi16)[ch] = __low2half(h);
-                q[kOffLo8 + ch] = static_cast<uint8_t>(lo & 0xff);
-                if (!(p.experiment & 16)) q[kOffHi8 + ch] = static_cast<uint8_t>(hi & 0xff);
+                reinterpret_cast<uint16_t*>(q + kOffP8)[ch] = e0;
               }
               if (store && p0 + i + 1 < kTok) {
                 uint8_t* q = rowp + (i + 1) * kRowBytes;
                 reinterpret_cast<__half*>(q + kOffHi16)[ch] = __high2half(h);
-                q[kOffLo8 + ch] = static_cast<uint8_t>(lo >> 8);
-                if (!(p.experiment & 16)) q[kOffHi8 + ch] = static_cast<uint8_t>(hi >> 8);
+                reinterpret_cast<uint16_t*>(q + kOffP8)[ch] = e1;
               }
             }
           } else {

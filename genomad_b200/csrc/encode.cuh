@@ -87,6 +87,7 @@ encode_tokens_kernel(const uint8_t* __restrict__ ascii, uint16_t* __restrict__ t
 constexpr int kEmbSeg = 256;
 constexpr int kEmbThreads = 256;
 constexpr int kTriple = 4096;
+static_assert(kEmbThreads == kEmbSeg, "embed_conv1_kernel computes one position's table codes per thread");
 
 template <bool kFromAscii>
 __global__ void __launch_bounds__(kEmbThreads)
@@ -94,10 +95,11 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
                    const float* __restrict__ table,   // [6][257][128]
                    const float* __restrict__ triple,  // [2][4096][128]: A-table, B-table
                    const float* __restrict__ bias,    // [128]
-                   uint8_t* __restrict__ y_out,       // [n][5997][768 B] activation rows (hi16 | lo16 | lo8 | hi8)
-                   int n_windows, DeviceStatus* status, int experiment) {
+                   uint8_t* __restrict__ y_out,       // [n][5997][768 B] activation rows (hi16 | lo16 | e4m3 pairs)
+                   int n_windows, DeviceStatus* status) {
   __shared__ int16_t s_tok[kEmbSeg + 8];    // s_tok[i] = token at position t0 - 5 + i, or -1 (causal pad)
   __shared__ uint8_t s_b[kEmbSeg + 16];
+  __shared__ int s_code[kEmbSeg];           // per position: (A code | B code << 16), 0xFFFF in a half = that half needs the 3-row fallback
   const int w = blockIdx.y;
   const int t0 = blockIdx.x * kEmbSeg;
   if (kFromAscii) {
@@ -123,6 +125,17 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
     }
   }
   __syncthreads();
+  // Triple-table codes once per position (one thread each) instead of once per lane of the warp that produces the row: the
+  // row loop below was issue-bound (83 % of the issue slots, ~115 warp instructions per position, a third of them this
+  // token logic executed redundantly by all 32 lanes).
+  {
+    const int i = threadIdx.x;                         // kEmbThreads == kEmbSeg
+    const int tk0 = s_tok[i], tk2 = s_tok[i + 2], tk3 = s_tok[i + 3], tk5 = s_tok[i + 5];
+    const int ca = (tk0 > 0 && tk2 > 0) ? (((tk0 - 1) << 4) | ((tk2 - 1) & 15)) : 0xFFFF;    // bases t-5 .. t all ACGT (implies tk1 > 0)
+    const int cb = (tk3 > 0 && tk5 > 0) ? (((tk3 - 1) << 4) | ((tk5 - 1) & 15)) : 0xFFFF;    // bases t-2 .. t+3 all ACGT (implies tk4 > 0)
+    s_code[i] = ca | (cb << 16);
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 b4 = reinterpret_cast<const float4*>(bias)[lane];
   const float4* tab4 = reinterpret_cast<const float4*>(table);
@@ -131,30 +144,22 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
     return tk >= 0 ? __ldg(tab4 + (static_cast<size_t>(j) * kVocab + tk) * (kC / 4) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   auto add4 = [](float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
-  for (int i = warp; i < kEmbSeg; i += kEmbThreads / 32) {
+  float amax = 0.f;
+  const int i_end = min(kEmbSeg, kTok - t0);
+  for (int i = warp; i < i_end; i += kEmbThreads / 32) {
     const int t = t0 + i;
-    if (t >= kTok) break;
-    int tk[kTaps];
-#pragma unroll
-    for (int j = 0; j < kTaps; ++j) tk[j] = s_tok[i + j];          // token at position t - 5 + j
+    const int code = s_code[i];
+    const int ca = code & 0xFFFF, cb = static_cast<unsigned>(code) >> 16;
     float4 A, B;
-    if (tk[0] > 0 && tk[2] > 0) {                                   // bases t-5 .. t all ACGT (implies tk[1] > 0)
-      const int code = ((tk[0] - 1) << 4) | ((tk[2] - 1) & 15);
-      A = __ldg(tri4 + static_cast<size_t>(code) * (kC / 4) + lane);
-    } else {
-      A = add4(add4(row(0, tk[0]), row(1, tk[1])), row(2, tk[2]));
-    }
-    if (tk[3] > 0 && tk[5] > 0) {                                   // bases t-2 .. t+3 all ACGT (implies tk[4] > 0)
-      const int code = ((tk[3] - 1) << 4) | ((tk[5] - 1) & 15);
-      B = __ldg(tri4 + (static_cast<size_t>(kTriple) + code) * (kC / 4) + lane);
-    } else {
-      B = add4(add4(row(3, tk[3]), row(4, tk[4])), row(5, tk[5]));
-    }
+    if (ca != 0xFFFF) A = __ldg(tri4 + static_cast<size_t>(ca) * (kC / 4) + lane);
+    else A = add4(add4(row(0, s_tok[i]), row(1, s_tok[i + 1])), row(2, s_tok[i + 2]));
+    if (cb != 0xFFFF) B = __ldg(tri4 + (static_cast<size_t>(kTriple) + cb) * (kC / 4) + lane);
+    else B = add4(add4(row(3, s_tok[i + 3]), row(4, s_tok[i + 4])), row(5, s_tok[i + 5]));
     float4 a = add4(A, B);
     // Y = 32 * y1; planes: hi16, lo16 (w_v, gather), lo8 / hi8 (conv2 correction passes)
     a.x = kActScale * lrelu(a.x + b4.x); a.y = kActScale * lrelu(a.y + b4.y);
     a.z = kActScale * lrelu(a.z + b4.z); a.w = kActScale * lrelu(a.w + b4.w);
-    flag_act_overflow(status, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), kHi8Limit, 1);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
     __half2 h01, h23, l01, l23;
     split2_f16(a.x, a.y, h01, l01);
     split2_f16(a.z, a.w, h23, l23);
@@ -165,14 +170,14 @@ embed_conv1_kernel(const uint8_t* __restrict__ ascii, const uint16_t* __restrict
         make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) =
         make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-    *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
-        static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, (a.y - f1) * kLo8Scale)) |
-        (static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, (a.w - f3) * kLo8Scale)) << 16);
-    if (!(experiment & 16))                 // timing experiment only: 16 = do not store the hi8 plane (results become wrong)
-      *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
-        static_cast<uint32_t>(pack_e4m3x2(f0 * kHi8Scale, f1 * kHi8Scale)) |
-        (static_cast<uint32_t>(pack_e4m3x2(f2 * kHi8Scale, f3 * kHi8Scale)) << 16);
+    // e4m3 pairs (lo8[c], hi8[c]) of this lane's 4 channels: 8 contiguous bytes
+    *reinterpret_cast<uint2*>(rowp + kOffP8 + lane * 8) = make_uint2(
+        static_cast<uint32_t>(pack_e4m3x2((a.x - f0) * kLo8Scale, f0 * kHi8Scale)) |
+            (static_cast<uint32_t>(pack_e4m3x2((a.y - f1) * kLo8Scale, f1 * kHi8Scale)) << 16),
+        static_cast<uint32_t>(pack_e4m3x2((a.z - f2) * kLo8Scale, f2 * kHi8Scale)) |
+            (static_cast<uint32_t>(pack_e4m3x2((a.w - f3) * kLo8Scale, f3 * kHi8Scale)) << 16));
   }
+  flag_act_overflow(status, amax, kHi8Limit, 1);
 }
 
 }  // namespace gnm

@@ -294,6 +294,9 @@ extern "C" int gnm_fasta_open(const char* path, int single_window, int threads, 
   }
   ::close(fd);
   build_index(f, threads);
+  // the index pass touched every page: drop them from the resident set (they stay in the page cache); the streaming phase
+  // faults in only what this rank extracts, and gnm_fasta_release_before lets go of it again behind the cursor
+  if (f->map_base) ::madvise(f->map_base, f->map_len, MADV_DONTNEED);
   *out = f;
   return 0;
 }

@@ -175,12 +175,11 @@ layer1_wv_kernel(const __grid_constant__ CUtensorMap tm_w, const FusedParams p) 
             uint8_t* rowp = p.y_out + (static_cast<size_t>(w) * kTok + t) * kRowBytes;
             *reinterpret_cast<uint2*>(rowp + kOffHi16 + lane * 8) = hv;
             *reinterpret_cast<uint2*>(rowp + kOffLo16 + lane * 8) = lv;
-            *reinterpret_cast<uint32_t*>(rowp + kOffLo8 + lane * 4) =
-                static_cast<uint32_t>(pack_e4m3x2((a.x - fa.x) * kLo8Scale, (a.y - fa.y) * kLo8Scale)) |
-                (static_cast<uint32_t>(pack_e4m3x2((a.z - fb.x) * kLo8Scale, (a.w - fb.y) * kLo8Scale)) << 16);
-            *reinterpret_cast<uint32_t*>(rowp + kOffHi8 + lane * 4) =
-                static_cast<uint32_t>(pack_e4m3x2(fa.x * kHi8Scale, fa.y * kHi8Scale)) |
-                (static_cast<uint32_t>(pack_e4m3x2(fb.x * kHi8Scale, fb.y * kHi8Scale)) << 16);
+            *reinterpret_cast<uint2*>(rowp + kOffP8 + lane * 8) = make_uint2(
+                static_cast<uint32_t>(pack_e4m3x2((a.x - fa.x) * kLo8Scale, fa.x * kHi8Scale)) |
+                    (static_cast<uint32_t>(pack_e4m3x2((a.y - fa.y) * kLo8Scale, fa.y * kHi8Scale)) << 16),
+                static_cast<uint32_t>(pack_e4m3x2((a.z - fb.x) * kLo8Scale, fb.x * kHi8Scale)) |
+                    (static_cast<uint32_t>(pack_e4m3x2((a.w - fb.y) * kLo8Scale, fb.y * kHi8Scale)) << 16));
           } else {
             hv = make_uint2(0u, 0u); lv = hv;          // columns past the window end: finite, ignored by the epilogue
           }

@@ -187,7 +187,7 @@ uint32_t gnm_crc32c(const void* data, size_t n);
  * "debug_stop" 0 = full pipeline, 1 = stop after layer 1 + gather#0, 2 = after conv2, 3 = after conv3;
  * "profile_stages" 1 = record a CUDA event between stages (see gnm_stage_times);
  * "conv_experiment" bit mask for timing experiments on the conv kernel: 2 = skip the epilogue's global stores (results
- * become wrong), 16 = layer 1 and conv2 do not store the derivable hi8 plane (upper bound of what dropping it from HBM could save), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg");
+ * become wrong), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg");
  * "fuse_l1" 1 = run layer 1 and the first IGLOO kernel's value projection as ONE kernel (csrc/layer1_wv.cuh: SIMT producers
  * write the tensor core's B operand straight into swizzled shared memory; bit-identical results, 17 instead of 18 launches
  * per step; measured slower than the two separate kernels at the end of round 1, hence 0 by default). */
