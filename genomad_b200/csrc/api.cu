@@ -546,6 +546,7 @@ static int launch_wv_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t s
   p.n_units = kNumBands * p.groups;
   p.status = h->status;
   p.experiment = h->conv_experiment;
+  p.dbg = (h->conv_experiment & 512) && s == 1 ? h->conv_dbg : nullptr;      // cycle counters of the IGLOO#1 launch
   const int grid = std::min(h->num_sms, p.n_units);
   if (wv_split(h, s, p.groups, grid, st)) return 1;
   p.cta_split = h->cta_split + s * (h->num_sms + 1);

@@ -17,22 +17,22 @@
 //     operands swapped so that D^T[cout][row]), but the four slab regions [8 windows][32 rows][128 B] come from ONE 3-D TMA
 //     box each, and the 64 KB of w_v weight stages stay resident in shared memory for the whole launch (the old kernel
 //     re-streamed them for every unit: a third of its L2 -> SM traffic).
-//   * patch gather: the same 8 warps that drain the accumulators first run the band's entries against the unit's 8 windows,
-//     reading the rows from the SLAB IN SHARED MEMORY that the TMA engine filled for the MMAs (the first version of this
-//     kernel re-read them from global memory / L2 with 16-byte loads: correct, but latency-bound at 8 row loads in flight
-//     per warp -- 1.68 ms per launch against 0.65 + 0.65 ms for the two separate kernels).  The gather follows the MMAs'
-//     K-half order so slab regions are still recycled one K-half at a time: pass 0 takes channels 0..63 from the hi16.k0 /
-//     lo16.k0 regions, pass 1 channels 64..127 from hi16.k1 / lo16.k1; a region goes back to the producer when both the
-//     tensor core (tcgen05.commit) and the 8 gather warps have arrived on its "empty" barrier (count 9).
+//   * patch gather: the 20 consumer warps that drain the accumulators first run the band's entries (<= 3 per warp) against the
+//     unit's 8 windows, reading the rows from the SLAB IN SHARED MEMORY that the TMA engine filled for the MMAs.  The gather
+//     follows the MMAs' K-half order so slab regions are still recycled one K-half at a time: pass 0 takes channels 0..63 from
+//     the hi16.k0 / lo16.k0 regions, pass 1 channels 64..127 from hi16.k1 / lo16.k1; a region goes back to the producer when
+//     both the tensor core (tcgen05.commit) and every consumer warp have arrived on its "empty" barrier (count 21).
 //     One LDS.128 per lane covers two windows of one entry: lanes 0-7 / 8-15 read the 128-byte hi / lo row of window 2i
 //     (16-byte chunk j of a row sits at chunk j ^ (row & 7): TMA's 128-byte swizzle), lanes 16-31 the same for window 2i+1;
-//     each quarter-warp reads one whole row, so the access is bank-conflict free.  The four partial sums per lane are
-//     reduced by a 5-shuffle transposing butterfly (fixed order -> deterministic); lanes 0,4,..,28 end up with the 8
-//     windows' values, park the pass-0 halves in a small shared scratch (or in part_t itself for bands with more than
-//     8 x 12 entries) and write part_t[slot][window] after pass 1.  The folded weights and in-band rows of the band's
-//     entries are staged in shared memory when a CTA moves to a band (28 KB, up to 56 entries; larger bands fall back
-//     to global loads): ncu on the first version showed the warps stalled on exactly those global loads.  patch_finish_t_kernel adds a patch's four slots in
-//     fixed order k = 0..3 plus the bias, as before.
+//     each quarter-warp reads one whole row, so the access is bank-conflict free.  A row that the warp's previous entry
+//     already pulled out is not read again (entries are sorted by position; 46 % share their row with a neighbour).  The four
+//     partial sums per lane are reduced by a 5-shuffle transposing butterfly (fixed order -> deterministic); lanes
+//     0,4,..,28 end up with the 8 windows' values and write part_t[slot][window] after pass 1 (the pass-0 halves wait in
+//     registers; bands with more than 60 entries take a generic path that parks them in part_t).
+//     patch_finish_t_kernel adds a patch's four slots in fixed order k = 0..3 plus the bias, as before.
+//   * what bounds it (profiles/r02_wv_gather_ncu.md): not HBM (48 % of peak) and not the gather's FMAs -- reading
+//     the rows WITHOUT any arithmetic costs the same -- but the shared-memory port that UMMA operand reads (288 KB per unit),
+//     TMA fills (131 KB) and the gather's LDS (~150 KB) share: ~650 cycles per (entry, K-half) in a consumer warp.
 //
 // Warp roles (768 threads, 1 CTA per SM):  warp 0 lane 0: weight loader (once) | warp 1: tcgen05.mma issuer |
 // warp 2: TMEM allocator | warp 3 lane 0: activation producer (TMA) | warps 4..23: patch gather, then epilogue
@@ -74,7 +74,8 @@ struct WvGatherParams {
   int groups;                  // window groups per band = n_pad / 8
   int n_units;                 // kNumBands * groups
   const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
-  int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores
+  int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows but does no arithmetic
+  long long* dbg;              // optional [gridDim.x][8] cycle counters (nullptr = off), see tools/ab_stages.py --wvg-cycles
   DeviceStatus* status;
 };
 
@@ -173,11 +174,14 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     int it = 0;
     uint32_t phases = 0;
     int b0 = 0;
+    long long m_wait_full = 0, m_wait_acc = 0, tq = 0;
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
       const uint32_t acc = tmem_base + as * 256;
+      if (p.dbg) tq = clock64();
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 520 + as);
+      if (p.dbg) m_wait_acc += clock64() - tq;
 #pragma unroll
       for (int q = 0; q < kWvStages; ++q) {
         // stage q = (K-half q/2, weight hi/lo q%2); hi-weight stages multiply both the hi16 and the lo16 region
@@ -185,8 +189,10 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         int bh = b0 + 2 * kh; if (bh >= kWgBufs) bh -= kWgBufs;               // hi16 region of this K-half
         int bl = b0 + 2 * kh + 1; if (bl >= kWgBufs) bl -= kWgBufs;           // lo16 region
         if ((q & 1) == 0) {
+          if (p.dbg) tq = clock64();
           mbar_wait(&a_full[bh], (phases >> bh) & 1, p.status, 530 + bh);
           mbar_wait(&a_full[bl], (phases >> bl) & 1, p.status, 536 + bl);
+          if (p.dbg) m_wait_full += clock64() - tq;
           phases ^= (1u << bh) | (1u << bl);
         }
         tc_fence_after();
@@ -208,6 +214,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 6] = m_wait_full; p.dbg[blockIdx.x * 8 + 7] = m_wait_acc; }
   } else if (warp >= 4) {
     // ===================================================================== patch gather, then accumulator epilogue
     const int gw = warp - 4;                                   // 0..19
@@ -237,6 +244,8 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     int it = 0;
     uint32_t phases = 0;
     int b0 = 0;
+    long long c_wait_full = 0, c_gather = 0, c_wait_acc = 0, c_epi = 0, tq = 0;
+    const long long t_begin = clock64();
     int cur_band = -1, e_begin = 0, cnt = 0;
     int rr[kWgWarpCap] = {0, 0, 0};                         // rows (inside the band) of this warp's entries, fast path
     bool fast = true;
@@ -245,9 +254,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       const int w0 = (unit - band * p.groups) * kBandWins;
       if (band != cur_band) {                                  // this warp's contiguous run of the band's entries
         cur_band = band;
-        const int b0 = p.band_start[band], b1 = p.band_start[band + 1];
-        const int per = (b1 - b0 + kWgWarps - 1) / kWgWarps;
-        e_begin = min(b1, b0 + gw * per);
+        const int s0 = p.band_start[band], b1 = p.band_start[band + 1];
+        const int per = (b1 - s0 + kWgWarps - 1) / kWgWarps;
+        e_begin = min(b1, s0 + gw * per);
         cnt = min(b1, e_begin + per) - e_begin;
         if (p.experiment & 32) cnt = 0;
         fast = per <= kWgWarpCap;
@@ -255,7 +264,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         for (int i = 0; i < kWgWarpCap; ++i) rr[i] = (fast && i < cnt) ? p.ent_pos[e_begin + i] - band * kBandRows : 0;
       }
       // ---------------- gather: this warp's entries x the unit's 8 windows, one K-half per pass.  Few entries per warp
-      // (16 warps share the band's ~45) keep the time a K-half's regions are held short: the slab is single-buffered, so
+      // (20 warps share the band's ~45) keep the time a K-half's regions are held short: the slab is single-buffered, so
       // the next unit's loads start only when every consumer has released a region.
       float c0[kWgWarpCap];                                    // pass-0 halves of the fast path (lanes with (lane & 3) == 0)
 #pragma unroll 1
@@ -266,23 +275,38 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         phases ^= (1u << bh) | (1u << bl);
         const uint32_t reg_base = slab + (plane ? bl : bh) * kWgRegion + wodd * (kBandRows * 128) + (jch << 4);
         if (fast) {
-          // the folded weights do not depend on the slab: request them (L1 / L2) BEFORE waiting for the TMA data
-          float4 wa[kWgWarpCap], wb[kWgWarpCap];
-#pragma unroll
-          for (int i = 0; i < kWgWarpCap; ++i)
-            if (i < cnt) {
-              const float* wp = p.ent_w + static_cast<size_t>(e_begin + i) * kC + kh * 64 + jch * 8;
-              wa[i] = ldg_weights(wp); wb[i] = ldg_weights(wp + 4);
-            }
+          if (p.dbg) tq = clock64();
           mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);          // hi16 K-half kh
           mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);          // lo16 K-half kh
+          if (p.dbg) { const long long t = clock64(); c_wait_full += t - tq; tq = t; }
+          // Entries are sorted by position and 46 % of them share their row with a neighbour (8,400 entries hit ~4,500
+          // distinct positions): a row that the previous entry of this warp already pulled out of the slab is not read again.
+          // (Timing experiment 256 -- rows read, no arithmetic -- costs as much as the full gather: the LDS traffic next to the
+          // MMAs' operand reads and the TMA fills is what the gather costs, not its FMAs.)
+          uint4 v[4];
 #pragma unroll
           for (int i = 0; i < kWgWarpCap; ++i)
             if (i < cnt) {
-              const uint32_t ad = (reg_base + rr[i] * 128) ^ ((rr[i] & 7) << 4);     // 128-byte swizzle: chunk j -> j ^ (row & 7)
-              float a[4];
+              if (i == 0 || rr[i] != rr[i - 1]) {
+                const uint32_t ad = (reg_base + rr[i] * 128) ^ ((rr[i] & 7) << 4);   // 128-byte swizzle: chunk j -> j ^ (row & 7)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) a[j] = dot8_h(lds128(ad + j * (2 * kBandRows * 128)), wa[i], wb[i]);
+                for (int j = 0; j < 4; ++j) v[j] = lds128(ad + j * (2 * kBandRows * 128));
+              }
+              // Folded weights of this entry and K-half through L1 / L2 (evict_last).  Staging them in shared memory instead
+              // (30 KB, private slots per warp) was measured and is slower (1.11 / 1.30 ms): the kernel's limit is the
+              // shared-memory port (UMMA operand reads 288 KB + TMA fills 131 KB + these LDS per unit ~ 95 of 128 B/cycle;
+              // cycle counters: ~650 cycles per (entry, K-half) in a consumer warp with everything in shared memory), so
+              // weight reads are better off on the L1 / L2 path.
+              const float* wp = p.ent_w + static_cast<size_t>(e_begin + i) * kC + kh * 64 + jch * 8;
+              const float4 wa = ldg_weights(wp), wb = ldg_weights(wp + 4);
+              float a[4];
+              if (p.experiment & 256) {                        // timing experiment: rows are read, no arithmetic
+                asm volatile("" :: "r"(v[0].x | v[1].x | v[2].x | v[3].x));
+                c0[i] = 0.f;
+                continue;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) a[j] = dot8_h(v[j], wa, wb);
               const float c = reduce4(a);
               if (kh == 0) c0[i] = c;
               else if ((lane & 3) == 0 && !(p.experiment & 64)) p.part_t[static_cast<size_t>(e_begin + i) * p.n_pad + w0 + wi_out] = c0[i] + c;
@@ -310,12 +334,15 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&a_empty[bh]); mbar_arrive(&a_empty[bl]); }           // this warp is done with the K-half's regions
+        if (p.dbg && fast) c_gather += clock64() - tq;
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
       // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g
       const int as = it & 1;
       const uint32_t accphase = (it >> 1) & 1;
+      if (p.dbg) tq = clock64();
       mbar_wait(&acc_full[as], accphase, p.status, 540 + as);
+      if (p.dbg) { const long long t = clock64(); c_wait_acc += t - tq; tq = t; }
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256;
 #pragma unroll 1
@@ -337,6 +364,11 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (p.dbg) c_epi += clock64() - tq;
+    }
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = c_wait_full; d[2] = c_gather; d[3] = c_wait_acc; d[4] = c_epi; d[5] = it;
     }
   }
 

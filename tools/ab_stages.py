@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--wvg-cycles", action="store_true", help="print the fused IGLOO kernel's per-CTA cycle breakdown (conv_experiment bit 512)")
     args = ap.parse_args()
     B = args.batch
     clf = engine.Classifier(None, device=0, max_batch=B)
@@ -66,6 +67,22 @@ def main():
                     base = pr
                 else:
                     print(f"    max |dp| vs first configuration: {(pr - base).abs().max().item():.2e}", flush=True)
+    if args.wvg_cycles:
+        clf.set_option("fuse_gather", 1)
+        wvg_cycles(clf, pool)
+
+
+def wvg_cycles(clf, pool):
+    names = ["consumer total", "consumer wait a_full", "consumer gather (LDS + math + release)", "consumer wait acc_full",
+             "consumer epilogue", "units", "MMA wait a_full", "MMA wait acc_empty"]
+    clf.set_option("conv_experiment", 512)
+    clf.predict_ascii(pool[0]); torch.cuda.synchronize()
+    d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
+    clf.set_option("conv_experiment", 0)
+    units = max(d[:, 5].mean(), 1)
+    print("wv_gather_kernel (IGLOO#1) cycle breakdown, mean over CTAs (warp 4 = one consumer warp; warp 1 = MMA issuer):")
+    for i, nm in enumerate(names):
+        print(f"   {nm:42s} {d[:, i].mean():12.0f}   per unit {d[:, i].mean() / units:9.0f}   (min {d[:, i].min():.0f}, max {d[:, i].max():.0f})")
 
 
 if __name__ == "__main__":
