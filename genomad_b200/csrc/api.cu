@@ -96,6 +96,16 @@ struct gnm_handle {
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
   float* out_stage[2] = {nullptr, nullptr};
+  // second set of the buffers that a step's main part writes and its tail reads (q, mpi + TF32 halves): with two sets the tail
+  // of step i (logits / attention / head, on tail_stream) overlaps the main part of step i+1 (tail_overlap, see forward_many)
+  float* q_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  float* mpi_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  float* mpi_hi_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  float* mpi_lo_set[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  CUtensorMap tm_lg_a_set[2][2][2];                  // [parity][igloo][hi/lo]
+  int tail_overlap = 1;                              // option: 1 = overlap (multi-step calls only), 0 = strictly in order
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t main_done[2] = {nullptr, nullptr}, tail_done[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
   DeviceStatus* status = nullptr;                    // pinned host memory, device-visible
@@ -356,10 +366,13 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   const size_t mbp = static_cast<size_t>(h->mb_pad);
   for (int i = 0; i < 2; ++i) {
     if (dev_alloc(h, &h->ybuf[i], mbp * kTok * kRowBytes)) return 1;      // whole window groups: wv_gather_kernel reads n_pad windows
-    if (dev_alloc(h, &h->q[i], mb * kPooled * kC)) return 1;
-    if (dev_alloc(h, &h->mpi[i], mb * kPatches)) return 1;
-    if (dev_alloc(h, &h->mpi_hi[i], mb * kPatches)) return 1;
-    if (dev_alloc(h, &h->mpi_lo[i], mb * kPatches)) return 1;
+    for (int par = 0; par < 2; ++par) {
+      if (dev_alloc(h, &h->q_set[par][i], mb * kPooled * kC)) return 1;
+      if (dev_alloc(h, &h->mpi_set[par][i], mb * kPatches)) return 1;
+      if (dev_alloc(h, &h->mpi_hi_set[par][i], mb * kPatches)) return 1;
+      if (dev_alloc(h, &h->mpi_lo_set[par][i], mb * kPatches)) return 1;
+    }
+    h->q[i] = h->q_set[0][i]; h->mpi[i] = h->mpi_set[0][i]; h->mpi_hi[i] = h->mpi_hi_set[0][i]; h->mpi_lo[i] = h->mpi_lo_set[0][i];
     if (dev_alloc(h, &h->in_stage[i], mb * kWindow)) return 1;
     if (dev_alloc(h, &h->out_stage[i], mb * 3)) return 1;
     GNM_CUDA(cudaEventCreateWithFlags(&h->in_ready[i], cudaEventDisableTiming));
@@ -380,6 +393,15 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (dev_alloc(h, &h->hA_lo[1], mb * kHidden)) return 1;
   GNM_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   GNM_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    GNM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GNM_CUDA(cudaStreamCreateWithPriority(&h->tail_stream, cudaStreamNonBlocking, prio_hi));   // few small CTAs: schedule them promptly
+    for (int i = 0; i < 2; ++i) {
+      GNM_CUDA(cudaEventCreateWithFlags(&h->main_done[i], cudaEventDisableTiming));
+      GNM_CUDA(cudaEventCreateWithFlags(&h->tail_done[i], cudaEventDisableTiming));
+    }
+  }
   GNM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->status), sizeof(DeviceStatus), cudaHostAllocMapped));
   std::memset(h->status, 0, sizeof(DeviceStatus));
 
@@ -395,8 +417,11 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (make_w_map(enc, &h->tm_w[2], h->wpack[2], kWvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[3], h->wpack[3], kWvStages)) return 1;
   for (int s = 0; s < 2; ++s) {
-    if (make_f32_map(enc, &h->tm_lg_a[s][0], h->mpi_hi[s], kPatches, max_batch, kLgBM)) return 1;
-    if (make_f32_map(enc, &h->tm_lg_a[s][1], h->mpi_lo[s], kPatches, max_batch, kLgBM)) return 1;
+    for (int par = 0; par < 2; ++par) {
+      if (make_f32_map(enc, &h->tm_lg_a_set[par][s][0], h->mpi_hi_set[par][s], kPatches, max_batch, kLgBM)) return 1;
+      if (make_f32_map(enc, &h->tm_lg_a_set[par][s][1], h->mpi_lo_set[par][s], kPatches, max_batch, kLgBM)) return 1;
+    }
+    h->tm_lg_a[s][0] = h->tm_lg_a_set[0][s][0]; h->tm_lg_a[s][1] = h->tm_lg_a_set[0][s][1];
     if (make_f32_map(enc, &h->tm_lg_b[s][0], h->wqkT_hi[s], kPatches, kPooled, kLgBN)) return 1;
     if (make_f32_map(enc, &h->tm_lg_b[s][1], h->wqkT_lo[s], kPatches, kPooled, kLgBN)) return 1;
   }
@@ -433,6 +458,11 @@ extern "C" int gnm_destroy(gnm_handle* h) {
     if (h->in_free[i]) cudaEventDestroy(h->in_free[i]);
   }
   for (cudaEvent_t e : h->timer.events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->main_done[i]) cudaEventDestroy(h->main_done[i]);
+    if (h->tail_done[i]) cudaEventDestroy(h->tail_done[i]);
+  }
+  if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
   if (h->status) cudaFreeHost(h->status);
@@ -657,9 +687,19 @@ static int launch_dense_tc(gnm_handle* h, int layer, int n, float* out, float* o
   return check_launch(h, "splitk_reduce_epi_kernel");
 }
 
-// One step: n <= max_batch windows, input either ASCII or tokens, output probs (device).
-static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
-                        cudaStream_t st) {
+// the buffer set the next step's main part writes and its tail reads (kernel arguments are captured at launch, so switching the
+// "current" pointers between steps is all it takes)
+static void select_set(gnm_handle* h, int par) {
+  for (int s = 0; s < 2; ++s) {
+    h->q[s] = h->q_set[par][s]; h->mpi[s] = h->mpi_set[par][s];
+    h->mpi_hi[s] = h->mpi_hi_set[par][s]; h->mpi_lo[s] = h->mpi_lo_set[par][s];
+    h->tm_lg_a[s][0] = h->tm_lg_a_set[par][s][0]; h->tm_lg_a[s][1] = h->tm_lg_a_set[par][s][1];
+  }
+}
+
+// main part of a step: layer 1, the two IGLOO kernels' value projection + patch gather, conv2, conv3 (everything that streams
+// the activations); returns 2 when a debug_stop cut the step short
+static int forward_main(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, cudaStream_t st) {
   dim3 egrid((kTok + kEmbSeg - 1) / kEmbSeg, n);
   h->ybuf_fp8lo[0] = h->ybuf_fp8lo[1] = 0;
   const bool fused = h->fuse_l1 && h->conv_impl == 0;       // layer 1 + w_v#0 in one kernel
@@ -688,7 +728,7 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     timer_mark(h, "gather0", st);
     if (launch_gather(h, 0, 0, n, st)) return 1;
   }
-  if (h->debug_stop == 1) { timer_mark(h, "end", st); return 0; }
+  if (h->debug_stop == 1) { timer_mark(h, "end", st); return 2; }
   if (h->conv_impl == 0) {
     if (!fused && !fg) {
       timer_mark(h, "wv0", st);
@@ -696,10 +736,10 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     }
     timer_mark(h, "conv2", st);
     if (launch_conv(h, 0, 0, n, st)) return 1;             // y1 (buf0) -> y2 (buf1)
-    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
+    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 2; }
     timer_mark(h, "conv3", st);
     if (launch_conv(h, 1, 1, n, st)) return 1;             // y2 (buf1) -> y3 (buf0)
-    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
+    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 2; }
     if (fg) {
       timer_mark(h, "wvg1", st);
       if (launch_wv_gather(h, 1, 0, n, st)) return 1;        // y3 (buf0) -> q1, mpi1
@@ -712,10 +752,10 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     if (launch_wv_ref(h, 0, 0, n, st)) return 1;
     timer_mark(h, "conv2(ref)", st);
     if (launch_conv_ref(h, 0, 0, n, st)) return 1;
-    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 0; }
+    if (h->debug_stop == 2) { timer_mark(h, "end", st); return 2; }
     timer_mark(h, "conv3(ref)", st);
     if (launch_conv_ref(h, 1, 1, n, st)) return 1;
-    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 0; }
+    if (h->debug_stop == 3) { timer_mark(h, "end", st); return 2; }
     timer_mark(h, "wv1(ref)", st);
     if (launch_wv_ref(h, 1, 0, n, st)) return 1;
   }
@@ -723,6 +763,12 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
     timer_mark(h, "gather1", st);
     if (launch_gather(h, 1, 0, n, st)) return 1;
   }
+  return 0;
+}
+
+// tail of a step: attention logits, softmax + weighted sum, dense head -> probabilities.  Small kernels (0.35 ms per 1024 windows)
+// that read only q / mpi of the current buffer set and the tail-only buffers (logits, h0..h2)
+static int forward_tail(gnm_handle* h, int n, float* d_probs, cudaStream_t st) {
   for (int s = 0; s < 2; ++s) {
     timer_mark(h, s ? "logits1" : "logits0", st);
     if (launch_logits(h, s, n, st)) return 1;
@@ -743,6 +789,47 @@ static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d
   timer_mark(h, "end", st);
   return 0;
 }
+
+// One step: n <= max_batch windows, strictly in order on one stream.
+static int forward_step(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs,
+                        cudaStream_t st) {
+  const int rc = forward_main(h, d_ascii, d_tok, n, st);
+  if (rc) return rc == 2 ? 0 : 1;
+  return forward_tail(h, n, d_probs, st);
+}
+
+// Steps of a multi-step call with the tails overlapped: the main part of step i+1 (which starts with the issue-bound layer-1
+// kernel, small CTAs, no dynamic shared memory) runs on `st` while the few small kernels of step i's tail run on the
+// high-priority tail_stream next to it.  Two buffer sets alternate; main(i) waits for tail(i-2) (same set), tail(i) waits for
+// main(i); `st` is joined with both tails before the call returns, so the caller's stream semantics are unchanged.
+struct TailOverlap {
+  gnm_handle* h; cudaStream_t st; int steps_done = 0;
+  bool on;
+  TailOverlap(gnm_handle* h_, cudaStream_t st_, int n_steps)
+      : h(h_), st(st_), on(h_->tail_overlap && n_steps > 1 && !h_->profile_stages && h_->debug_stop == 0) {}
+  int step(const uint8_t* d_ascii, const uint16_t* d_tok, int n, float* d_probs, cudaStream_t* tail_out = nullptr) {
+    if (tail_out) *tail_out = st;
+    if (!on) return forward_step(h, d_ascii, d_tok, n, d_probs, st);
+    const int par = steps_done & 1;
+    select_set(h, par);
+    if (steps_done >= 2) GNM_CUDA(cudaStreamWaitEvent(st, h->tail_done[par], 0));
+    const int rc = forward_main(h, d_ascii, d_tok, n, st);
+    if (rc) return 1;
+    GNM_CUDA(cudaEventRecord(h->main_done[par], st));
+    GNM_CUDA(cudaStreamWaitEvent(h->tail_stream, h->main_done[par], 0));
+    if (forward_tail(h, n, d_probs, h->tail_stream)) return 1;
+    if (tail_out) *tail_out = h->tail_stream;
+    GNM_CUDA(cudaEventRecord(h->tail_done[par], h->tail_stream));
+    ++steps_done;
+    return 0;
+  }
+  int join() {                                           // `st` continues only after every tail has finished
+    if (!on) return 0;
+    for (int k = 0; k < 2 && k < steps_done; ++k) GNM_CUDA(cudaStreamWaitEvent(st, h->tail_done[(steps_done - 1 - k) & 1], 0));
+    select_set(h, (steps_done - 1) & 1);                 // debug_fetch sees the last step's buffers
+    return 0;
+  }
+};
 
 static int check_device_status(gnm_handle* h) {
   if (h->status && h->status->act_overflow) {
@@ -771,13 +858,13 @@ static int forward_any(gnm_handle* h, const uint8_t* d_ascii, const uint16_t* d_
   GNM_CUDA(cudaSetDevice(h->device));
   if (check_device_status(h)) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TailOverlap ov(h, st, (n + h->max_batch - 1) / h->max_batch);
   for (int off = 0; off < n; off += h->max_batch) {
     const int m = std::min(h->max_batch, n - off);
-    if (forward_step(h, d_ascii ? d_ascii + static_cast<size_t>(off) * kWindow : nullptr,
-                     d_tok ? d_tok + static_cast<size_t>(off) * kTok : nullptr, m,
-                     d_probs + static_cast<size_t>(off) * 3, st)) return 1;
+    if (ov.step(d_ascii ? d_ascii + static_cast<size_t>(off) * kWindow : nullptr,
+                d_tok ? d_tok + static_cast<size_t>(off) * kTok : nullptr, m, d_probs + static_cast<size_t>(off) * 3)) return 1;
   }
-  return 0;
+  return ov.join();
 }
 
 extern "C" int gnm_forward_ascii(gnm_handle* h, const uint8_t* d_ascii, int n, float* d_probs, void* stream) {
@@ -846,6 +933,7 @@ extern "C" int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, f
   if (check_device_status(h)) return 1;
   const int mb = h->max_batch;
   const int steps = (n + mb - 1) / mb;
+  TailOverlap ov(h, h->compute_stream, steps);
   for (int i = 0; i < steps; ++i) {
     const int b = i & 1;
     const int off = i * mb;
@@ -855,12 +943,18 @@ extern "C" int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, f
                              static_cast<size_t>(m) * kWindow, cudaMemcpyHostToDevice, h->copy_stream));
     GNM_CUDA(cudaEventRecord(h->in_ready[b], h->copy_stream));
     GNM_CUDA(cudaStreamWaitEvent(h->compute_stream, h->in_ready[b], 0));
-    if (forward_step(h, h->in_stage[b], nullptr, m, h->out_stage[b], h->compute_stream)) return 1;
+    cudaStream_t tail = h->compute_stream;               // the stream that produced out_stage[b] (tail_stream when overlapped)
+    if (ov.step(h->in_stage[b], nullptr, m, h->out_stage[b], &tail)) return 1;
+    // the input stage is only read by layer 1, but the event sits after the step's main part (the same stream); the output
+    // stage of parity b is rewritten by the tail of step i+2, which is ordered after this copy on the same stream
     GNM_CUDA(cudaEventRecord(h->in_free[b], h->compute_stream));
     GNM_CUDA(cudaMemcpyAsync(h_probs + static_cast<size_t>(off) * 3, h->out_stage[b], static_cast<size_t>(m) * 3 * sizeof(float),
-                             cudaMemcpyDeviceToHost, h->compute_stream));
+                             cudaMemcpyDeviceToHost, tail));
+    if (ov.on) GNM_CUDA(cudaEventRecord(h->tail_done[b], tail));     // re-record: the buffer set is free once the copy is queued behind the tail
   }
+  if (ov.join()) return 1;
   GNM_CUDA(cudaStreamSynchronize(h->compute_stream));
+  if (ov.on) GNM_CUDA(cudaStreamSynchronize(h->tail_stream));
   return check_device_status(h);
 }
 
@@ -873,6 +967,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   else if (k == "conv_experiment") h->conv_experiment = value;
   else if (k == "fuse_l1") h->fuse_l1 = value ? 1 : 0;
   else if (k == "fuse_gather") h->fuse_gather = value ? 1 : 0;
+  else if (k == "tail_overlap") h->tail_overlap = value ? 1 : 0;
   else if (k == "conv_cluster") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail("conv_cluster must be 1, 2, 4 or 8"); h->conv_cluster = value; }
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);
@@ -886,6 +981,7 @@ extern "C" int gnm_get_option(gnm_handle* h, const char* name, int* value) {
   else if (k == "profile_stages") *value = h->profile_stages;
   else if (k == "fuse_l1") *value = h->fuse_l1;
   else if (k == "fuse_gather") *value = h->fuse_gather;
+  else if (k == "tail_overlap") *value = h->tail_overlap;
   else if (k == "max_batch") *value = h->max_batch;
   else if (k == "num_sms") *value = h->num_sms;
   else return fail("unknown option: " + k);

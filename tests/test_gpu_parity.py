@@ -539,3 +539,29 @@ def test_fused_wv_gather_vs_separate_kernels(shipped):
             assert np.abs(res[0][0] - res[1][0]).max() <= 5e-6, n
     finally:
         clf.close()
+
+
+def test_tail_overlap_is_invisible(shipped):
+    """Multi-step calls run each step's tail (logits / attention / dense head) on a second stream next to the following step's
+    main part, alternating two buffer sets.  The result must be bitwise what the strictly ordered execution gives -- device
+    entry point and host entry point, batch counts that end on either buffer set, live IGLOO weights."""
+    from genomad_b200.engine import Classifier
+    a = _families(7 * 16 + 5, seed=23)                                     # 8 internal steps of 16, the last one partial
+    clf = Classifier(M.synthetic_igloo_weights(shipped), device=0, max_batch=16)
+    try:
+        at = torch.from_numpy(a).cuda()
+        res = {}
+        for ov in (1, 0):
+            clf.set_option("tail_overlap", ov)
+            p_dev = clf.predict_ascii(at).cpu().numpy()
+            p_dev2 = clf.predict_ascii(at[:48]).cpu().numpy()              # 3 steps: ends on the other buffer set
+            p_host = clf.classify_host(a)
+            clf.check_status()
+            res[ov] = (p_dev, p_dev2, p_host)
+        for x, y in zip(res[0], res[1]):
+            assert np.array_equal(x, y)
+        assert np.array_equal(res[1][0], res[1][2]) and np.array_equal(res[1][0][:48], res[1][1])
+        one = np.concatenate([clf.predict_ascii(at[i:i + 16]).cpu().numpy() for i in range(0, len(a), 16)])
+        assert np.array_equal(one, res[1][0])                              # single-step calls (never overlapped) agree too
+    finally:
+        clf.close()

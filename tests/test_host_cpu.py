@@ -423,3 +423,32 @@ def test_native_fasta_streaming_block_export(tmp_path):
     pf.release_before(n)
     assert np.array_equal(pf.export_windows(0, 5, buf), ref.windows[:5])
     pf.close()
+
+
+def test_bench_synthetic_fasta_and_stream_helpers(tmp_path):
+    """bench.py's synthetic inputs: the FASTA writer's window arithmetic agrees with the reader (configs 1 and 4 shapes in
+    miniature), and the counter-based window stream is a pure function of (seed, index) on NumPy and on torch alike."""
+    import importlib.util
+    import torch
+    from pathlib import Path as _P
+    spec = importlib.util.spec_from_file_location("bench_mod", _P(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from genomad_b200 import synth
+    for n_contigs, ln, exact in ((7, 10_000, True), (3, 100_000, False), (5, 8_499, False), (2, 2_000, True)):
+        fa = tmp_path / f"b_{ln}.fna"
+        bench.write_fasta(fa, n_contigs, ln, seed=0, exact_rng=exact)
+        pf = sequence.ParsedFasta(fa)
+        assert pf.check() and pf.n_contigs == n_contigs and pf.n_windows == bench.count_windows(ln, n_contigs)
+        assert list(pf.index().names) == [f"contig_{i:03d}" for i in range(n_contigs)]
+        pf.close()
+    idx = np.array([0, 1, 999_999, 123_456])
+    a = synth.windows_numpy(idx, seed=1)
+    assert a.shape == (4, 6000) and set(np.unique(a)) <= set(b"ACGTNR")
+    assert np.array_equal(a[3], synth.windows_numpy([123_456], seed=1)[0])             # pure function of the index
+    assert not np.array_equal(a[0], synth.windows_numpy([0], seed=2)[0])               # ... and of the seed
+    t = synth.windows_torch(123_455, 3, 1, "cpu").numpy()
+    assert np.array_equal(t, synth.windows_numpy(np.arange(123_455, 123_458), seed=1))
+    sub = synth.subsample_indices(256, 100_000, seed=1)
+    assert len(sub) == 256 == len(set(sub.tolist())) and np.all(np.diff(sub) > 0)
+    assert (synth.windows_numpy(sub, seed=1) == ord("N")).any(1).sum() >= 4                # the dirty sub-stream is represented

@@ -24,12 +24,16 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--steps-per-call", type=int, default=1, help="internal steps per API call (> 1 exercises the tail overlap)")
     ap.add_argument("--wvg-cycles", action="store_true", help="print the fused IGLOO kernel's per-CTA cycle breakdown (conv_experiment bit 512)")
     args = ap.parse_args()
     B = args.batch
     clf = engine.Classifier(None, device=0, max_batch=B)
     pool = [synth.windows_torch(1000 * i, B, 1, "cuda") for i in range(3)]
     out = torch.empty((B, 3), dtype=torch.float32, device="cuda")
+    spc = max(1, args.steps_per_call)
+    big = torch.cat([pool[i % 3] for i in range(spc)]) if spc > 1 else None
+    big_out = torch.empty((spc * B, 3), dtype=torch.float32, device="cuda") if spc > 1 else None
     base = None
     for rep in range(2):                                       # two rounds: the second is at the settled clock
         for cfg in args.configs:
@@ -37,6 +41,7 @@ def main():
                 clf.set_option(k, 0)
             clf.set_option("fuse_gather", 1)
             clf.set_option("conv_cluster", 1)
+            clf.set_option("tail_overlap", 1)
             for kv in cfg.split(","):
                 k, v = kv.split("=")
                 clf.set_option(k, int(v))
@@ -45,11 +50,17 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for i in range(args.steps):
-                clf.predict_ascii(pool[i % 3], out)
+            if spc > 1:
+                for i in range(max(1, args.steps // spc)):
+                    clf.predict_ascii(big, big_out)
+                n_steps = max(1, args.steps // spc) * spc
+            else:
+                for i in range(args.steps):
+                    clf.predict_ascii(pool[i % 3], out)
+                n_steps = args.steps
             e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / args.steps
+            ms = e0.elapsed_time(e1) / n_steps
             clf.set_option("profile_stages", 1)
             for i in range(6):
                 clf.predict_ascii(pool[i % 3], out)
