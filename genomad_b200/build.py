@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-    "-lcudart", "-Xcompiler", "-pthread",
+    "-lcudart", "-Xcompiler", "-pthread", "-lz",
 ]
 
 

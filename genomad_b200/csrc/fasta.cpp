@@ -45,6 +45,13 @@
 
 #include "../../include/gnm.h"
 
+#if defined(__has_include)
+#if __has_include(<zlib.h>)
+#include <zlib.h>
+#define GNM_HAVE_ZLIB 1
+#endif
+#endif
+
 namespace {
 
 constexpr int64_t kWin = GNM_WINDOW, kMinTail = 2500, kMaxN = 4000;
@@ -89,6 +96,7 @@ struct gnm_fasta {
   int single_window = 0;
   void* map_base = nullptr;        // mmap'ed file (gnm_fasta_open) or nullptr (caller memory)
   size_t map_len = 0;
+  std::unique_ptr<uint8_t[]> owned;   // inflated text of a gzip input (gnm_fasta_open_gz)
   std::vector<Record> recs;        // every record found (before dropping empties)
   std::vector<int64_t> kept;       // indices of records whose stripped sequence is non-empty
   std::vector<int64_t> kept_first; // first_window of every kept record (sorted; binary search window -> record)
@@ -299,6 +307,120 @@ extern "C" int gnm_fasta_open(const char* path, int single_window, int threads, 
   if (f->map_base) ::madvise(f->map_base, f->map_len, MADV_DONTNEED);
   *out = f;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ gzip input
+// gzip / BGZF FASTA -> text in memory -> index.  A gzip stream cannot be entered in the middle, so compressed input is
+// inflated completely (the reference does the same through Python's gzip module, utils.py:155-171); what is native here:
+//   * BGZF files (bgzip, the block-compressed gzip dialect of htslib: every <= 64 KB block is its own gzip member and carries
+//     its compressed size in a "BC" extra field, its inflated size in its trailer) are inflated block-parallel on `threads`
+//     threads straight into their final positions;
+//   * plain gzip (single or concatenated members) is inflated sequentially by zlib with the output pre-sized from the trailer.
+extern "C" int gnm_fasta_open_gz(const char* path, int single_window, int threads, gnm_fasta** out) {
+  if (!out || !path) { g_fasta_err = "gnm_fasta_open_gz: null argument"; return 1; }
+#ifndef GNM_HAVE_ZLIB
+  g_fasta_err = "gnm_fasta_open_gz: libgnm was built without zlib";
+  return 1;
+#else
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) { g_fasta_err = std::string("gnm_fasta_open_gz: cannot open ") + path + ": " + std::strerror(errno); return 1; }
+  struct stat st;
+  if (::fstat(fd, &st) != 0 || st.st_size < 18) { g_fasta_err = "gnm_fasta_open_gz: not a gzip file"; ::close(fd); return 1; }
+  const size_t clen = static_cast<size_t>(st.st_size);
+  void* m = ::mmap(nullptr, clen, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (m == MAP_FAILED) { g_fasta_err = std::string("gnm_fasta_open_gz: mmap failed: ") + std::strerror(errno); return 1; }
+  const uint8_t* c = static_cast<const uint8_t*>(m);
+  struct Unmap { void* p; size_t n; ~Unmap() { ::munmap(p, n); } } unmap{m, clen};
+  if (c[0] != 0x1f || c[1] != 0x8b) { g_fasta_err = "gnm_fasta_open_gz: not a gzip file"; return 1; }
+  auto rd16 = [&](size_t o) { return static_cast<uint32_t>(c[o]) | (static_cast<uint32_t>(c[o + 1]) << 8); };
+  auto rd32 = [&](size_t o) { return rd16(o) | (rd16(o + 2) << 16); };
+  // ---- BGZF?  header: 1f 8b 08 04 .. XLEN=6 'B' 'C' 02 00 BSIZE(2)
+  std::vector<size_t> blk_off, blk_out;
+  std::vector<uint32_t> blk_clen, blk_ulen;
+  bool bgzf = true;
+  {
+    size_t o = 0, total = 0;
+    while (o < clen) {
+      if (o + 18 > clen || c[o] != 0x1f || c[o + 1] != 0x8b || c[o + 2] != 8 || !(c[o + 3] & 4) || rd16(o + 10) != 6 ||
+          c[o + 12] != 'B' || c[o + 13] != 'C' || rd16(o + 14) != 2) { bgzf = false; break; }
+      const size_t bsize = static_cast<size_t>(rd16(o + 16)) + 1;
+      if (bsize < 26 || o + bsize > clen) { bgzf = false; break; }
+      const uint32_t ulen = rd32(o + bsize - 4);
+      blk_off.push_back(o); blk_clen.push_back(static_cast<uint32_t>(bsize)); blk_ulen.push_back(ulen); blk_out.push_back(total);
+      total += ulen;
+      o += bsize;
+    }
+    if (bgzf) blk_out.push_back(total);
+  }
+  gnm_fasta* f = new gnm_fasta();
+  f->single_window = single_window;
+  if (bgzf && !blk_off.empty()) {
+    const size_t total = blk_out.back();
+    f->owned.reset(new uint8_t[total + 1]);
+    std::atomic<int> bad{0};
+    parallel_for(static_cast<int64_t>(blk_off.size()), threads, [&](int64_t b) {
+      if (blk_ulen[b] == 0) return;                        // the empty end-of-file marker block
+      z_stream zs;
+      std::memset(&zs, 0, sizeof zs);
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+      zs.next_in = const_cast<Bytef*>(c + blk_off[b] + 18);
+      zs.avail_in = blk_clen[b] - 18 - 8;
+      zs.next_out = f->owned.get() + blk_out[b];
+      zs.avail_out = blk_ulen[b];
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) bad = 1;
+      inflateEnd(&zs);
+    });
+    if (bad) { delete f; g_fasta_err = "gnm_fasta_open_gz: corrupt BGZF block"; return 1; }
+    f->len = static_cast<int64_t>(total);
+  } else {
+    // plain gzip, possibly several concatenated members; zlib's counters are 32-bit, so input and output are fed in <= 1 GiB pieces
+    size_t cap = std::max<size_t>(static_cast<size_t>(rd32(clen - 4)) + 64, clen * 3), n = 0, in_off = 0;
+    std::unique_ptr<uint8_t[]> buf(new uint8_t[cap]);
+    z_stream zs;
+    std::memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) { delete f; g_fasta_err = "gnm_fasta_open_gz: inflateInit2 failed"; return 1; }
+    bool ok = true, done = false;
+    constexpr size_t kPiece = size_t(1) << 30;
+    while (!done) {
+      if (zs.avail_in == 0 && in_off < clen) {
+        const size_t piece = std::min(kPiece, clen - in_off);
+        zs.next_in = const_cast<Bytef*>(c + in_off);
+        zs.avail_in = static_cast<uInt>(piece);
+        in_off += piece;
+      }
+      if (n == cap) {                                        // grow the output geometrically
+        const size_t ncap = cap * 2;
+        std::unique_ptr<uint8_t[]> nb(new uint8_t[ncap]);
+        std::memcpy(nb.get(), buf.get(), n);
+        buf.swap(nb); cap = ncap;
+      }
+      const size_t room = std::min(kPiece, cap - n);
+      zs.next_out = buf.get() + n;
+      zs.avail_out = static_cast<uInt>(room);
+      const uInt in_before = zs.avail_in;
+      const int rc = inflate(&zs, Z_NO_FLUSH);
+      const size_t produced = room - zs.avail_out;
+      n += produced;
+      if (rc == Z_STREAM_END) {                              // one member finished: another one may follow
+        const bool more = zs.avail_in > 0 || in_off < clen;
+        const uint8_t next = zs.avail_in > 0 ? *zs.next_in : (in_off < clen ? c[in_off] : 0);
+        if (more && next == 0x1f) inflateReset(&zs); else done = true;
+      } else if (rc == Z_OK || rc == Z_BUF_ERROR) {
+        if (produced == 0 && zs.avail_in == in_before && zs.avail_in == 0 && in_off >= clen) { ok = false; done = true; }   // truncated
+      } else { ok = false; done = true; }
+    }
+    inflateEnd(&zs);
+    if (!ok) { delete f; g_fasta_err = "gnm_fasta_open_gz: corrupt or truncated gzip stream"; return 1; }
+    f->owned.swap(buf);
+    f->len = static_cast<int64_t>(n);
+  }
+  f->text = f->owned.get();
+  build_index(f, threads);
+  *out = f;
+  return 0;
+#endif
 }
 
 extern "C" int gnm_fasta_info(const gnm_fasta* f, int64_t* n_records_nonempty, int* has_duplicate_ids, int64_t* n_contigs,

@@ -19,8 +19,8 @@ Unlike the reference (a Python generator of ``Sequence`` objects feeding a per-w
 production path (``ParsedFasta`` / ``encode_fasta``) is native code in libgnm.so (csrc/fasta.cpp): a
 multi-threaded INDEX pass over the mmap'ed file (O(records) state, no copy), after which any block of the global
 window list is exported straight from the file text into pinned uint8 [n, 6000] chunks that are shipped to the
-GPU as they are -- tokenisation happens on the device (csrc/encode.cuh).  Compressed inputs are decompressed by
-Python's zlib/bz2/lzma bindings (C speed) into memory first.  ``iter_fasta`` / ``window_spans`` /
+GPU as they are -- tokenisation happens on the device (csrc/encode.cuh).  gzip input is inflated natively into
+memory (BGZF files block-parallel on all reader threads); bz2 / xz / zstd go through Python's bindings.  ``iter_fasta`` / ``window_spans`` /
 ``encode_fasta_py`` are the readable pure-Python statement of the same rules; the tests hold the native code
 to them and both to golden vectors made with the real reference.
 """
@@ -180,9 +180,13 @@ class ParsedFasta:
         avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         self._threads = max(1, min(int(threads), avail, 32)) if threads else min(32, avail)    # --threads is honoured (32 saturate the reader)
         self._h = C.c_void_p()
-        if is_compressed(path) == Compression.uncompressed:
+        kind = is_compressed(path)
+        if kind == Compression.uncompressed:
             self._text = None                               # mmap inside the library: the file is never copied
             rc = self._lib.gnm_fasta_open(str(path).encode(), int(bool(single_window)), self._threads, C.byref(self._h))
+        elif kind == Compression.gzip:
+            self._text = None                               # inflated natively (BGZF: block-parallel), owned by the library
+            rc = self._lib.gnm_fasta_open_gz(str(path).encode(), int(bool(single_window)), self._threads, C.byref(self._h))
         else:
             self._text = read_bytes(path)                   # decompressed text, kept alive: the index points into it
             buf = self._text

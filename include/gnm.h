@@ -139,6 +139,8 @@ int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_pro
  * FASTA -> windows, INDEX then STREAM (csrc/fasta.cpp).  Replaces the Python loop read_fasta(strip_n=True) ->
  * seq_windows(6000, 2500) -> N rule -> upper-case + pad (sequence.py:96-167, nn_classification.py:65-72).
  *   gnm_fasta_open   : plain (uncompressed) FASTA file; the file is mmap'ed, never copied into anonymous memory.
+ *   gnm_fasta_open_gz: gzip / BGZF FASTA: inflated into library-owned memory (BGZF block-parallel on `threads` threads, plain gzip
+ *                      sequentially by zlib), then indexed like the others.
  *   gnm_fasta_parse  : FASTA text in caller memory (decompressed input; `len` bytes, must stay alive until gnm_fasta_free).
  *                      Both build the same multi-threaded index: O(records) state, no copy of the sequences.
  *   gnm_fasta_info   : n_records_nonempty / has_duplicate_ids are what check_fasta() tests (sequence.py:124-131);
@@ -154,6 +156,7 @@ int gnm_classify_host(gnm_handle* h, const uint8_t* h_ascii, int n, float* h_pro
 typedef struct gnm_fasta gnm_fasta;
 const char* gnm_fasta_last_error(void);
 int gnm_fasta_open(const char* path, int single_window, int threads, gnm_fasta** out);
+int gnm_fasta_open_gz(const char* path, int single_window, int threads, gnm_fasta** out);
 int gnm_fasta_parse(const uint8_t* text, size_t len, int single_window, int threads, gnm_fasta** out);
 int gnm_fasta_info(const gnm_fasta* f, int64_t* n_records_nonempty, int* has_duplicate_ids, int64_t* n_contigs,
                    int64_t* n_windows, int64_t* header_bytes);

@@ -452,3 +452,50 @@ def test_bench_synthetic_fasta_and_stream_helpers(tmp_path):
     sub = synth.subsample_indices(256, 100_000, seed=1)
     assert len(sub) == 256 == len(set(sub.tolist())) and np.all(np.diff(sub) > 0)
     assert (synth.windows_numpy(sub, seed=1) == ord("N")).any(1).sum() >= 4                # the dirty sub-stream is represented
+
+
+def _bgzf(data: bytes, block: int = 65280) -> bytes:
+    """BGZF (bgzip) container: independent gzip members with a 'BC' extra field carrying the block size, plus the empty EOF block."""
+    import struct
+    import zlib
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if i is None else data[i:i + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        bsize = 18 + len(comp) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk))
+    return bytes(out)
+
+
+def test_native_gzip_and_bgzf_inputs(tmp_path):
+    """gzip input is inflated natively (csrc/fasta.cpp: gnm_fasta_open_gz): single member, concatenated members and BGZF
+    (block-parallel) must give exactly the windows of the plain file; a truncated stream is an error, not a short read."""
+    rng = np.random.default_rng(31)
+    recs = []
+    for i, ln in enumerate([30000, 6100, 250000, 2600, 9000]):
+        t = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.choice(9, ln, p=[.23, .23, .23, .23, .02, .02, .01, .01, .02])].tobytes().decode()
+        recs.append(f">g{i} x\n" + "\n".join(t[k:k + 60] for k in range(0, ln, 60)) + "\n")
+    text = "".join(recs).encode()
+    plain = tmp_path / "p.fna"
+    plain.write_bytes(text)
+    ref = sequence.encode_fasta(plain)
+    cut = len(recs[0]) + len(recs[1]) + 1000                      # member boundary in the middle of a record
+    variants = {"single.fna.gz": gzip.compress(text), "multi.fna.gz": gzip.compress(text[:cut]) + gzip.compress(text[cut:]),
+                "bgzf.fna.gz": _bgzf(text), "bgzf_small.fna.gz": _bgzf(text, block=4096)}
+    for name, blob in variants.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        assert gzip.decompress(blob) == text, name                 # the fixtures are valid gzip for any reader
+        for th in (1, 5):
+            pf = sequence.ParsedFasta(p, threads=th)
+            assert pf._text is None                                 # native path, not Python's gzip
+            e = pf.encode()
+            assert list(e.names) == list(ref.names) and np.array_equal(e.offsets, ref.offsets), name
+            assert np.array_equal(e.windows, ref.windows), name
+            pf.close()
+    bad = tmp_path / "trunc.fna.gz"
+    bad.write_bytes(gzip.compress(text)[:-200])
+    with pytest.raises(RuntimeError):
+        sequence.ParsedFasta(bad)
