@@ -565,3 +565,26 @@ def test_tail_overlap_is_invisible(shipped):
         assert np.array_equal(one, res[1][0])                              # single-step calls (never overlapped) agree too
     finally:
         clf.close()
+
+
+def test_adversarial_patch_sets(shipped):
+    """The C ABI accepts any patch indices in [0, 5997).  Two extreme sets against the oracle: (a) every patch reads the same four
+    positions at the two ends of the window (two position bands of the fused IGLOO kernel hold all 8,400 entries: its generic
+    path, the cost-balanced CTA split and the finish kernel at their worst), (b) every patch reads one position four times."""
+    from genomad_b200 import engine
+    base = M.synthetic_igloo_weights(shipped, seed=11)
+    a = _families(11, seed=41)
+    tok = T.tokenize_windows(a)
+    for name, rows in (("ends", [0, 1, 5995, 5996]), ("one position x4", [3001, 3001, 3001, 3001])):
+        w = dict(base)
+        for s in (0, 1):
+            w[f"ig{s}_random_patches"] = np.tile(np.asarray(rows, np.int32).reshape(1, 4, 1), (2100, 1, 1))
+        ref = _oracle_probs(tok, w)
+        c = engine.Classifier(w, device=0, max_batch=16)
+        try:
+            p = c.predict_ascii(torch.from_numpy(a).cuda()).cpu().numpy()
+            c.check_status()
+        finally:
+            c.close()
+        assert np.abs(p - ref).max() <= TOL, (name, np.abs(p - ref).max())
+        assert np.array_equal(p.argmax(1), ref.argmax(1)), name
