@@ -7,4 +7,4 @@ Public surface (mirrors the reference's for this path only):
   genomad_b200.cli.nn_classification                                 <- `genomad nn-classification`
   genomad_b200.engine.Classifier                                     <- create_classifier() + predict()
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -37,7 +37,7 @@ static int fail(const std::string& m) { g_err = m; return 1; }
   } while (0)
 
 extern "C" const char* gnm_last_error(void) { return g_err.c_str(); }
-extern "C" const char* gnm_version(void) { return "libgnm 0.3 (sm_100a; tcgen05 fp16 + e4m3 split convs, fp16x3 w_v, tf32x3 logits)"; }
+extern "C" const char* gnm_version(void) { return "libgnm 0.3 (sm_100a; tcgen05 fp16 + e4m3 split convs, fused fp16x3 w_v + patch gather, tf32x3 logits and dense head)"; }
 
 // ------------------------------------------------------------------------------------------------
 struct StageTimer {
