@@ -62,6 +62,14 @@
 //              exchange that halves the store count was measured and brought nothing);
 //       w_v  : the max over 8 consecutive positions is a max over 8 registers (no shuffles); a warp writes
 //              128 contiguous bytes of q[g][:] per pooled row.
+//
+// Round 2: (i) the two e4m3 planes are interleaved as (lo8, hi8) pairs per channel (common.cuh), so the correction passes are one
+// K = 256 contraction per tap against weights interleaved the same way and conv2's epilogue needs one 2-byte store per position
+// instead of two 1-byte stores (conv2 2.30 -> 2.21 ms, profiles/r02_ab_pairs_interleaved.log); (ii) the epilogue tracks the largest
+// |Y| it produced and raises DeviceStatus::act_overflow beyond the operand formats' range; (iii) launching the persistent grid as
+// thread-block clusters of 2 / 4 (hoping L2 would merge the CTAs' identical weight-stage requests) was measured and is slower
+// (2.29 -> 2.40 / 2.43-2.49 ms, option conv_cluster, profiles/r02_ab_conv_cluster.log); (iv) the steady state of the whole step is
+// power-bound (1 kW cap, ~1.45-1.5 GHz during this kernel): tensor pipe 63-68 % active at that clock.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
