@@ -55,6 +55,8 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
+  int wv_tmem_a = 0;        // experiment: fused IGLOO kernel reads its w_v weights (A operand) from tensor memory
+  uint32_t* wv_t16[2] = {nullptr, nullptr};          // [2 hi/lo][128 cout][64 packed fp16 pairs along k] of w_v^T
   int conv_cluster = 1;     // experiment: thread-block cluster size of the conv kernel's launch (1 = no clusters)
   int fuse_gather = 1;      // 1 = w_v + patch gather in one pass over the activations (wv_gather.cuh); 0 = conv_t_kernel<true> + patch_stream_kernel
   int fuse_l1 = 0;          // 1 = layer 1 and w_v#0 in one kernel (layer1_wv.cuh; bit-identical, measured slower: off); 0 = embed_conv1_kernel + conv_t_kernel<true>
@@ -280,6 +282,22 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
       for (int kh = 0; kh < 2; ++kh)
         for (int w_lo = 0; w_lo < 2; ++w_lo) pack_stage_f16(pk, w->igloo[s].w_v, w_lo, kh, 1.f);
       if (dev_upload(h, &h->wpack[2 + s], pk.data(), pk.size())) return 1;
+      {   // the same weights as the TMEM-resident A operand: w_v^T [cout][k], fp16 hi and lo, two k per 32-bit word
+        std::vector<uint32_t> t16(static_cast<size_t>(2) * kC * 64);
+        for (int part = 0; part < 2; ++part)
+          for (int n = 0; n < kC; ++n)
+            for (int kp = 0; kp < 64; ++kp) {
+              uint32_t word = 0;
+              for (int e = 0; e < 2; ++e) {
+                const float x = w->igloo[s].w_v[static_cast<size_t>(2 * kp + e) * kC + n];
+                const __half hi = __float2half_rn(x);
+                const __half v = part ? __float2half_rn(x - __half2float(hi)) : hi;
+                word |= static_cast<uint32_t>(__half_as_ushort(v)) << (16 * e);
+              }
+              t16[(static_cast<size_t>(part) * kC + n) * 64 + kp] = word;
+            }
+        if (dev_upload(h, &h->wv_t16[s], t16.data(), t16.size())) return 1;
+      }
     }
     if (dev_upload(h, &h->conv_bias[0], w->conv2_bias, kC)) return 1;
     if (dev_upload(h, &h->conv_bias[1], w->conv3_bias, kC)) return 1;
@@ -577,6 +595,7 @@ static int launch_wv_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t s
   p.status = h->status;
   p.experiment = h->conv_experiment;
   p.dbg = (h->conv_experiment & 512) && s == 1 ? h->conv_dbg : nullptr;      // cycle counters of the IGLOO#1 launch
+  p.wv_t16 = h->wv_t16[s]; p.ts_mode = h->wv_tmem_a;
   const int grid = std::min(h->num_sms, p.n_units);
   if (wv_split(h, s, p.groups, grid, st)) return 1;
   p.cta_split = h->cta_split + s * (h->num_sms + 1);
@@ -968,6 +987,7 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   else if (k == "fuse_l1") h->fuse_l1 = value ? 1 : 0;
   else if (k == "fuse_gather") h->fuse_gather = value ? 1 : 0;
   else if (k == "tail_overlap") h->tail_overlap = value ? 1 : 0;
+  else if (k == "wv_tmem_a") h->wv_tmem_a = value ? 1 : 0;
   else if (k == "conv_cluster") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail("conv_cluster must be 1, 2, 4 or 8"); h->conv_cluster = value; }
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);

@@ -75,6 +75,8 @@ struct WvGatherParams {
   int n_units;                 // kNumBands * groups
   const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
   int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows but does no arithmetic
+  const uint32_t* wv_t16;      // [2 hi/lo][128 cout][64] packed fp16 pairs of w_v^T (A operand from tensor memory, ts_mode)
+  int ts_mode;                 // 1 = w_v weights live in TMEM (columns 256..383), one accumulator; 0 = weights in shared memory, two accumulators
   long long* dbg;              // optional [gridDim.x][8] cycle counters (nullptr = off), see tools/ab_stages.py --wvg-cycles
   DeviceStatus* status;
 };
@@ -127,7 +129,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     tma_prefetch_desc(&tm_band);
     tma_prefetch_desc(&tm_w);
     for (int i = 0; i < kWgBufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the consumer warps
-    mbar_init(w_full, 1);
+    mbar_init(w_full, p.ts_mode ? 4 : 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kWgWarps); }
     fence_barrier_init();
   }
@@ -140,11 +142,34 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  if (p.ts_mode && warp >= 4 && warp < 8) {
+    // ===================================================================== weights -> tensor memory (once): thread = output
+    // channel (TMEM lane), columns 256..319 = fp16(w_v^T) hi as 64 packed pairs along k, 320..383 = lo
+    const int cout = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int part = 0; part < 4; ++part) {                  // (hi, lo) x (k 0..63, k 64..127): 32 columns each
+      const uint32_t* src = p.wv_t16 + (static_cast<size_t>(part >> 1) * kC + cout) * 64 + (part & 1) * 32;
+      uint32_t r[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        r[i] = v.x; r[i + 1] = v.y; r[i + 2] = v.z; r[i + 3] = v.w;
+      }
+      tmem_st_32x32(lane_addr + 256 + part * 32, r);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_full);
+  }
   if (warp == 0 && lane == 0) {
     // ===================================================================== weights: loaded once, resident
-    const uint64_t pol = l2_policy_evict_last();
-    mbar_arrive_expect_tx(w_full, kWgWeights);
-    for (int q = 0; q < kWvStages; ++q) tma_load_2d_hint(s_w + q * kBStage, &tm_w, w_full, 0, q * 128, pol);
+    if (!p.ts_mode) {
+      const uint64_t pol = l2_policy_evict_last();
+      mbar_arrive_expect_tx(w_full, kWgWeights);
+      for (int q = 0; q < kWvStages; ++q) tma_load_2d_hint(s_w + q * kBStage, &tm_w, w_full, 0, q * 128, pol);
+    }
   } else if (warp == 3 && lane == 0) {
     // ===================================================================== activation producer
     const uint64_t pol = l2_policy_evict_first();
@@ -171,13 +196,15 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     const uint32_t a_base = smem_u32(s_a);
     const uint32_t w_base = smem_u32(s_w);
     mbar_wait(w_full, 0, p.status, 510);
+    tc_fence_after();
+    const bool ts = p.ts_mode != 0;
     int it = 0;
     uint32_t phases = 0;
     int b0 = 0;
     long long m_wait_full = 0, m_wait_acc = 0, tq = 0;
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
-      const int as = it & 1;
-      const uint32_t accphase = (it >> 1) & 1;
+      const int as = ts ? 0 : (it & 1);                      // ts_mode: the second accumulator's columns hold the weights
+      const uint32_t accphase = ts ? (it & 1) : ((it >> 1) & 1);
       const uint32_t acc = tmem_base + as * 256;
       if (p.dbg) tq = clock64();
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 520 + as);
@@ -201,10 +228,19 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
           const uint64_t y0 = desc0 + ((a_base + bh * kWgRegion) >> 4);                      // B: hi16 rows
           const uint64_t y1 = desc0 + ((a_base + bl * kWgRegion) >> 4);                      // B: lo16 rows
           const bool w_lo = (q & 1) != 0;
+          if (ts) {
+            const uint32_t wt = tmem_base + 256 + (w_lo ? 64 : 0) + kh * 32;                 // 16 k-elements = 8 columns per MMA
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
-            if (!w_lo) umma_f16(acc, wdesc + kk * 2, y1 + kk * 2, kIdesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16_ts(acc, wt + kk * 8, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+              if (!w_lo) umma_f16_ts(acc, wt + kk * 8, y1 + kk * 2, kIdesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+              if (!w_lo) umma_f16(acc, wdesc + kk * 2, y1 + kk * 2, kIdesc, 1u);
+            }
           }
           if (!w_lo) umma_commit(&a_empty[bl]);                  // the lo16 region is only used by the hi-weight stage
           else umma_commit(&a_empty[bh]);
@@ -338,8 +374,8 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
       // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g
-      const int as = it & 1;
-      const uint32_t accphase = (it >> 1) & 1;
+      const int as = p.ts_mode ? 0 : (it & 1);
+      const uint32_t accphase = p.ts_mode ? (it & 1) : ((it >> 1) & 1);
       if (p.dbg) tq = clock64();
       mbar_wait(&acc_full[as], accphase, p.status, 540 + as);
       if (p.dbg) { const long long t = clock64(); c_wait_acc += t - tq; tq = t; }

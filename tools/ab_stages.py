@@ -42,6 +42,7 @@ def main():
             clf.set_option("fuse_gather", 1)
             clf.set_option("conv_cluster", 1)
             clf.set_option("tail_overlap", 1)
+            clf.set_option("wv_tmem_a", 0)
             for kv in cfg.split(","):
                 k, v = kv.split("=")
                 clf.set_option(k, int(v))
