@@ -87,13 +87,17 @@ struct gnm_handle {
   CUtensorMap tm_lg_a[2][2];                         // [igloo][hi/lo] over mpi_hi / mpi_lo
   CUtensorMap tm_lg_b[2][2];                         // [igloo][hi/lo] over wqkT_hi / wqkT_lo
   float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products ([kGsSlots][mb_pad] in the fused path)
-  int32_t* band_start[2] = {nullptr, nullptr};       // [kNumBands + 1] first entry slot of every 32-position band
-  std::vector<int32_t> band_count[2];                // host copy: entries per band (cost model of wv_gather_kernel's unit split)
+  int2* grp[2] = {nullptr, nullptr};                 // wv_gather_kernel: position groups {first entry slot, row in band | entries << 8}
+  int32_t* band_gstart[2] = {nullptr, nullptr};      // [kNumBands + 1] first position group of every 32-position band
+  uint4* wfrag[2] = {nullptr, nullptr};              // [kGsSlots][2][4][4] folded weights as mma.m16n8k16 B fragments (fp16 hi / lo halves)
+  float gather_unscale[2] = {1.f, 1.f};              // 1 / the power of two applied to the folded weights before the fp16 split
+  std::vector<int32_t> band_groups[2];               // host copy: position groups per band (cost model of wv_gather_kernel's unit split)
   int32_t* cta_split = nullptr;                      // [num_sms + 1] device: unit range per CTA of the current launch
   std::vector<int32_t> split_host[2];                // host copy of the last split per IGLOO kernel (source of the async upload)
   int split_groups[2] = {-1, -1}, split_grid[2] = {-1, -1};
+  float wv_cost_base = 1.f, wv_cost_group = 0.1f;    // unit cost model of wv_split: base + per position group of the busiest warp
   int mb_pad = 0;                                    // max_batch rounded up to a multiple of 8 (window groups of wv_gather_kernel)
-  CUtensorMap tm_band[2];                            // activations, box = 128 B x 32 rows x 8 windows
+  CUtensorMap tm_band[2];                            // activations, box = 128 B x 8 windows x 32 positions (make_band_map)
   float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
@@ -157,6 +161,21 @@ static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activations) failed: " + std::to_string(int(r)));
+  return 0;
+}
+// wv_gather_kernel's view of the activations: the WINDOW axis is listed before the POSITION axis (strides need not ascend), so
+// the box {128 B, 8 windows, 32 positions} lands in shared memory as [position][window][128 B]: the 8 windows of one position are
+// one 1024-byte swizzle atom -- what the gather's ldmatrix wants -- and the 256 rows are still one K-major N = 256 UMMA operand.
+// Checked on B200 incl. the zero fill of positions >= 5997: tools/tma_order_probe.cu.
+static int make_band_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows) {
+  cuuint64_t dims[3] = {kRowBytes, static_cast<cuuint64_t>(n_windows), kTok};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(kTok) * kRowBytes, kRowBytes};
+  cuuint32_t box[3] = {128, kBandWins, kBandRows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation bands) failed: " + std::to_string(int(r)));
   return 0;
 }
 // packed weights [stages*128 rows][128 B]; box = 128 B x 128 rows
@@ -320,16 +339,55 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
         ent_w[slot * kC + c] = (g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c]) * (1.f / kActScale);
     }
     {
-      std::vector<int32_t> bs(kNumBands + 1, 0);             // ent_pos is sorted: band b = slots with position in [32b, 32b + 32)
+      // wv_gather_kernel's view of the same sorted entries: POSITION GROUPS = the entries that sit on one position, at most
+      // kWgGroupMax = 8 per group (the N of the warp-level mma the gather runs on; 8,400 entries hit ~4,500 positions), and the
+      // folded weights as that instruction's B fragments: fp16 hi / lo halves of w * 2^k (k moves the largest weight to ~2^14 so
+      // that the lo halves stay in fp16's normal range; the kernel multiplies the sums by 2^-k).
+      float wmax = 0.f;
+      for (float v : ent_w) wmax = std::max(wmax, std::fabs(v));
+      int k2 = 0;
+      if (wmax > 0.f && std::isfinite(wmax)) { int ex; std::frexp(wmax, &ex); k2 = std::max(-24, std::min(40, 14 - ex)); }   // wmax * 2^k2 in [2^13, 2^14)
+      const float wscale = std::ldexp(1.f, k2);
+      h->gather_unscale[s] = std::ldexp(1.f, -k2);
+      std::vector<int2> groups;
+      std::vector<int32_t> gs(kNumBands + 1, 0);
+      const size_t n_ent = order.size();
       size_t slot = 0;
-      for (int b = 0; b <= kNumBands; ++b) {
-        while (slot < order.size() && ent_pos[slot] < b * kBandRows) ++slot;
-        bs[b] = static_cast<int32_t>(slot);
+      for (int b = 0; b < kNumBands; ++b) {
+        gs[b] = static_cast<int32_t>(groups.size());
+        while (slot < n_ent && ent_pos[slot] < (b + 1) * kBandRows) {
+          size_t run = slot;
+          while (run < n_ent && ent_pos[run] == ent_pos[slot] && run - slot < static_cast<size_t>(kWgGroupMax)) ++run;
+          groups.push_back(make_int2(static_cast<int>(slot), (ent_pos[slot] - b * kBandRows) | (static_cast<int>(run - slot) << 8)));
+          slot = run;
+        }
       }
-      bs[kNumBands] = static_cast<int32_t>(order.size());
-      if (dev_upload(h, &h->band_start[s], bs.data(), bs.size())) return 1;
-      h->band_count[s].resize(kNumBands);
-      for (int b = 0; b < kNumBands; ++b) h->band_count[s][b] = bs[b + 1] - bs[b];
+      gs[kNumBands] = static_cast<int32_t>(groups.size());
+      if (groups.empty()) groups.push_back(make_int2(0, 0));
+      h->band_groups[s].resize(kNumBands);
+      for (int b = 0; b < kNumBands; ++b) h->band_groups[s][b] = gs[b + 1] - gs[b];
+      auto h2 = [](float x, float y) {
+        return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(x))) | (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(y))) << 16);
+      };
+      std::vector<uint32_t> frag(static_cast<size_t>(kGsSlots) * 128, 0u);      // 512 B per entry slot
+      for (size_t e = 0; e < n_ent; ++e)
+        for (int kh = 0; kh < 2; ++kh)
+          for (int ks = 0; ks < 4; ++ks)
+            for (int tig = 0; tig < 4; ++tig) {
+              const int k0 = kh * 64 + ks * 16 + 2 * tig;
+              const int kk[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+              float hi[4], lo[4];
+              for (int i = 0; i < 4; ++i) {
+                const float x = ent_w[e * kC + kk[i]] * wscale;
+                hi[i] = __half2float(__float2half_rn(x));
+                lo[i] = x - hi[i];
+              }
+              uint32_t* f = &frag[(((e * 2 + kh) * 4 + ks) * 4 + tig) * 4];
+              f[0] = h2(hi[0], hi[1]); f[1] = h2(hi[2], hi[3]); f[2] = h2(lo[0], lo[1]); f[3] = h2(lo[2], lo[3]);
+            }
+      if (dev_upload(h, &h->grp[s], groups.data(), groups.size())) return 1;
+      if (dev_upload(h, &h->band_gstart[s], gs.data(), gs.size())) return 1;
+      if (dev_upload(h, reinterpret_cast<uint32_t**>(&h->wfrag[s]), frag.data(), frag.size())) return 1;
     }
     if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
     if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
@@ -428,7 +486,7 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   if (get_encode_fn(&enc)) return 1;
   for (int i = 0; i < 2; ++i) {
     if (make_act_map(enc, &h->tm_act[i], h->ybuf[i], max_batch)) return 1;
-    if (make_act_map(enc, &h->tm_band[i], h->ybuf[i], h->mb_pad, kBandRows, kBandWins)) return 1;
+    if (make_band_map(enc, &h->tm_band[i], h->ybuf[i], h->mb_pad)) return 1;
   }
   if (make_w_map(enc, &h->tm_w[0], h->wpack[0], kConvStages)) return 1;
   if (make_w_map(enc, &h->tm_w[1], h->wpack[1], kConvStages)) return 1;
@@ -565,7 +623,11 @@ static int wv_split(gnm_handle* h, int s, int groups, int grid, cudaStream_t st)
   if (h->split_groups[s] == groups && h->split_grid[s] == grid) return 0;
   std::vector<double> cost(kNumBands);
   double total = 0;
-  for (int b = 0; b < kNumBands; ++b) { cost[b] = 0.73 + 0.37 * h->band_count[s][b] / 44.7; total += cost[b] * groups; }
+  for (int b = 0; b < kNumBands; ++b) {
+    const int per_warp = (h->band_groups[s][b] + kWgWarps - 1) / kWgWarps;
+    cost[b] = h->wv_cost_base + h->wv_cost_group * per_warp;
+    total += cost[b] * groups;
+  }
   std::vector<int32_t>& sp = h->split_host[s];
   sp.assign(h->num_sms + 1, kNumBands * groups);
   sp[0] = 0;
@@ -587,7 +649,7 @@ static int wv_split(gnm_handle* h, int s, int groups, int grid, cudaStream_t st)
 static int launch_wv_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t st) {
   WvGatherParams p;
   p.q_out = h->q[s]; p.out_scale = 1.f / kActScale;
-  p.ent_pos = h->ent_pos[s]; p.ent_w = h->ent_w[s]; p.band_start = h->band_start[s]; p.part_t = h->part;
+  p.grp = h->grp[s]; p.band_gstart = h->band_gstart[s]; p.wfrag = h->wfrag[s]; p.gather_unscale = h->gather_unscale[s]; p.part_t = h->part;
   p.n_windows = n;
   p.n_pad = (n + kBandWins - 1) / kBandWins * kBandWins;
   p.groups = p.n_pad / kBandWins;
@@ -988,6 +1050,10 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   else if (k == "fuse_gather") h->fuse_gather = value ? 1 : 0;
   else if (k == "tail_overlap") h->tail_overlap = value ? 1 : 0;
   else if (k == "wv_tmem_a") h->wv_tmem_a = value ? 1 : 0;
+  else if (k == "wv_cost_group") {      // experiment: per-mille cost of one position group per warp in wv_split's unit cost model (base = 1000)
+    if (value < 0 || value > 10000) return fail("wv_cost_group must be in [0, 10000]");
+    h->wv_cost_group = value * 1e-3f; h->split_groups[0] = h->split_groups[1] = -1;
+  }
   else if (k == "conv_cluster") { if (value != 1 && value != 2 && value != 4 && value != 8) return fail("conv_cluster must be 1, 2, 4 or 8"); h->conv_cluster = value; }
   else if (k == "profile_stages") { h->profile_stages = value ? 1 : 0; h->timer.names.clear(); }   // (re)starts the record
   else return fail("unknown option: " + k);

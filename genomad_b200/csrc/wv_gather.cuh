@@ -56,50 +56,50 @@ constexpr int kWgBufs     = 4;                                    // region buff
                                                                   // so the slab stays at exactly one unit
 constexpr int kWgSlab     = kWgBufs * kWgRegion;                  // hi16.k0 | lo16.k0 | hi16.k1 | lo16.k1        = 131072
 constexpr int kWgWeights  = kWvStages * kBStage;                  // resident w_v stages                         =  65536
-constexpr int kWgWarps    = 20;                                   // consumer warps: patch gather + accumulator epilogue
-constexpr int kWgThreads  = (4 + kWgWarps) * 32;                  // 768
-constexpr int kWgWarpCap  = 3;                                    // entries per warp on the fast path (60 per band; mean 45)
+constexpr int kWgWarps    = 12;                                   // patch-gather warps
+constexpr int kWgEpiWarps = 8;                                    // accumulator-epilogue warps (two per TMEM lane quarter)
+constexpr int kWgThreads  = (4 + kWgWarps + kWgEpiWarps) * 32;    // 768
+constexpr int kWgGroupCap = 3;                                    // position groups per warp on the fast path (36 per band; a band has <= 32
+                                                                  // positions, so only positions with more than 4 entries can exceed it)
+constexpr int kWgGroupMax = 4;                                    // entries per position group: the 8 columns of mma.m16n8k16 = 4 entries x (hi, lo)
 constexpr int kWgSmem     = kWgSlab + kWgWeights + 2048;          //                                                   = 198656
 static_assert(kWgSmem <= 232448, "wv_gather_kernel exceeds the 227 KB of shared memory a CTA may use");
+static_assert(kWgWarps % 4 == 0 && kWgEpiWarps == 8 && kBandRows / kPool == 4, "epilogue warp (quarter wq, half eh) takes pool groups eh and eh + 2");
 static_assert(kBandRows * kBandWins == 256, "one unit = one N = 256 tile");
 
 struct WvGatherParams {
   float* q_out;                // [n][749][128]
   float out_scale;             // 1/32 (activation scale)
-  const int32_t* ent_pos;      // [kGsSlots] position of each entry slot, sorted ascending
-  const float* ent_w;          // [kGsSlots][128] folded weights / 32
-  const int32_t* band_start;   // [kNumBands + 1] first entry slot of every band
+  const int2* grp;             // [groups of all bands] {first entry slot, row inside the band | entries << 8}: the entries (<= 8) on one position
+  const int32_t* band_gstart;  // [kNumBands + 1] first position group of every band
+  const uint4* wfrag;          // [kGsSlots][2 K-halves][4 k-steps][4 tig] folded weights * 2^k as mma.m16n8k16 B fragments {hi b0, hi b1, lo b0, lo b1}: a lane reads the (b0, b1) pair of its column
+  float gather_unscale;        // 1 / (power of two that moved the folded weights into fp16's normal range)
   float* part_t;               // [kGsSlots][n_pad] per-entry dot products (slot-major: a unit's 8 windows are contiguous)
   int n_windows, n_pad;        // n_pad = n rounded up to a multiple of 8
   int groups;                  // window groups per band = n_pad / 8
   int n_units;                 // kNumBands * groups
   const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
-  int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows but does no arithmetic
+  int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows and weights but does no arithmetic, 1024 = no weight loads, 2048 = no ldmatrix
   const uint32_t* wv_t16;      // [2 hi/lo][128 cout][64] packed fp16 pairs of w_v^T (A operand from tensor memory, ts_mode)
   int ts_mode;                 // 1 = w_v weights live in TMEM (columns 256..383), one accumulator; 0 = weights in shared memory, two accumulators
   long long* dbg;              // optional [gridDim.x][8] cycle counters (nullptr = off), see tools/ab_stages.py --wvg-cycles
   DeviceStatus* status;
 };
 
-__device__ __forceinline__ float4 ldg_weights(const float* p) {      // folded weights: keep them in L1 across units
-  float4 v;
-  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+__device__ __forceinline__ uint2 ldg_frag(const uint2* p) {          // folded-weight fragments: keep them in L1 across units
+  uint2 v;
+  asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-  return v;
+// four 8x8 fp16 matrices; lanes 8i..8i+7 give the row addresses of matrix i, register i of lane l = matrix i [l / 4][2 (l % 4) .. +1]
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t (&a)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(saddr));
 }
-__device__ __forceinline__ float dot8_h(const uint4& v, const float4& a, const float4& b) {
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
-  float s = __low2float(h[0]) * a.x;
-  s = fmaf(__high2float(h[0]), a.y, s);
-  s = fmaf(__low2float(h[1]), a.z, s); s = fmaf(__high2float(h[1]), a.w, s);
-  s = fmaf(__low2float(h[2]), b.x, s); s = fmaf(__high2float(h[2]), b.y, s);
-  s = fmaf(__low2float(h[3]), b.z, s); s = fmaf(__high2float(h[3]), b.w, s);
-  return s;
+// D[16x8] += A[16x16] * B[16x8], fp16 operands, fp32 accumulation (warp-level tensor-core instruction)
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -128,9 +128,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_band);
     tma_prefetch_desc(&tm_w);
-    for (int i = 0; i < kWgBufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the consumer warps
+    for (int i = 0; i < kWgBufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the gather warps
     mbar_init(w_full, p.ts_mode ? 4 : 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kWgWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kWgEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -186,7 +186,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         mbar_arrive_expect_tx(&a_full[b], kWgRegion);
         // k: 0 hi16 channels 0-63, 1 lo16 channels 0-63, 2 hi16 channels 64-127, 3 lo16 channels 64-127 (byte offset in the row)
         const int src = (k & 1 ? kOffLo16 : kOffHi16) + (k >> 1) * 128;
-        tma_load_3d_hint(s_a + b * kWgRegion, &tm_band, &a_full[b], src, band * kBandRows, w0, pol);
+        tma_load_3d_hint(s_a + b * kWgRegion, &tm_band, &a_full[b], src, w0, band * kBandRows, pol);     // box = {128 B, 8 windows, 32 positions}
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }
@@ -251,150 +251,154 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }
     if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 6] = m_wait_full; p.dbg[blockIdx.x * 8 + 7] = m_wait_acc; }
-  } else if (warp >= 4) {
-    // ===================================================================== patch gather, then accumulator epilogue
-    const int gw = warp - 4;                                   // 0..19
-    const int wq = warp & 3;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
-    const int grp = gw >> 2;                                   // epilogue: windows grp and grp+5 of the unit
-    const int ch = wq * 32 + lane;
-    const float oscale = p.out_scale;
-    // gather lane roles: quarter-warp (lane >> 3): 0 = hi row of the even window, 1 = lo row of the even window,
-    // 2 / 3 = the same for the odd window of the pair; chunk j = lane & 7 = channels 8j .. 8j+7 of the current K-half
-    const int jch = lane & 7;
-    const int plane = (lane >> 3) & 1;                         // 0 hi16, 1 lo16
-    const int wodd = lane >> 4;                                // window 2i + wodd of pair i
-    const bool up8 = lane & 8, up4 = lane & 4;
-    const int wi_out = ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + (lane >> 4);      // window this lane ends up holding
+  } else if (warp >= 4 && warp < 4 + kWgWarps) {
+    // ===================================================================== patch gather
+    const int gw = warp - 4;                                   // 0..11
+    const float gscale = p.gather_unscale;
+    // Gather lane roles.  ldmatrix: lanes 8i..8i+7 address matrix i = (plane i & 1: 0 hi16 / 1 lo16, 16-byte chunk i >> 1 of the
+    // k-step), row lane & 7 = window.  The A fragment then holds rows 0..7 = the 8 windows' hi16 halves and rows 8..15 = their
+    // lo16 halves; mma: gid = lane >> 2 = window (A / D row) = entry (B column), tig = lane & 3.
+    const int lm_plane = (lane >> 3) & 1, lm_chunk = lane >> 4, lm_win = lane & 7;
+    const int gid = lane >> 2, tig = lane & 3;
     const uint32_t slab = smem_u32(s_a);
-    // 4 partial sums (window pairs 0..3) of one entry -> the total of window wi_out in the lanes with (lane & 3) == 0:
-    // transposing butterfly over the 16 lanes that share a window, fixed order (deterministic)
-    auto reduce4 = [&](const float (&a)[4]) -> float {
-      float b0, b1, c;
-      { const float g = up8 ? a[0] : a[1], k = up8 ? a[1] : a[0]; b0 = k + __shfl_xor_sync(0xffffffffu, g, 8); }
-      { const float g = up8 ? a[2] : a[3], k = up8 ? a[3] : a[2]; b1 = k + __shfl_xor_sync(0xffffffffu, g, 8); }
-      { const float g = up4 ? b0 : b1, k = up4 ? b1 : b0; c = k + __shfl_xor_sync(0xffffffffu, g, 4); }
-      c += __shfl_xor_sync(0xffffffffu, c, 2);
-      c += __shfl_xor_sync(0xffffffffu, c, 1);
-      return c;
-    };
     int it = 0;
     uint32_t phases = 0;
     int b0 = 0;
-    long long c_wait_full = 0, c_gather = 0, c_wait_acc = 0, c_epi = 0, tq = 0;
+    long long c_wait_full = 0, c_gather = 0, tq = 0;
     const long long t_begin = clock64();
-    int cur_band = -1, e_begin = 0, cnt = 0;
-    int rr[kWgWarpCap] = {0, 0, 0};                         // rows (inside the band) of this warp's entries, fast path
+    int cur_band = -1, g_first = 0, g_cnt = 0, n_mine = 0;
+    int my_e0[kWgGroupCap] = {0, 0, 0}, my_meta[kWgGroupCap] = {0, 0, 0};     // this warp's position groups of the band, fast path
     bool fast = true;
+    // One position group x one K-half: D[16 x 8] = A[16 x 64] * B[64 x 8] as 4 k-steps (two independent chains of 2 mma).  B's
+    // columns are (entry 0 hi, entry 0 lo, entry 1 hi, ...): the fp16 hi / lo halves of up to 4 entries' folded weights.  Returns
+    // entry tig of window gid: (hi16 row + lo16 row) x (hi-weight column + lo-weight column).
+    auto gather_group = [&](int e0, int meta, int kh, uint32_t hi_base, uint32_t lo_base) -> float {
+      const int row = meta & 31, ne = meta >> 8;
+      const uint2* wf = reinterpret_cast<const uint2*>(p.wfrag) + ((static_cast<size_t>(e0 + (gid >> 1)) * 2 + kh) * 16 + tig) * 2 + (gid & 1);
+      uint2 b[4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) b[ks] = ((gid >> 1) < ne && !(p.experiment & 1024)) ? ldg_frag(wf + ks * 8) : make_uint2(0u, 0u);
+      const uint32_t rb = (lm_plane ? lo_base : hi_base) + row * (kBandWins * 128) + lm_win * 128;
+      uint32_t a[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (p.experiment & 2048) { a[ks][0] = a[ks][1] = a[ks][2] = a[ks][3] = rb; continue; }
+        ldsm_x4(rb + (((ks * 2 + lm_chunk) ^ lm_win) << 4), a[ks]);     // 128-byte swizzle: chunk j -> j ^ (row & 7)
+      }
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.experiment & 256) {                              // timing experiment: rows and weights are read, no arithmetic
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) asm volatile("" :: "r"(a[ks][0] | a[ks][1] | a[ks][2] | a[ks][3] | b[ks].x | b[ks].y));
+      } else {
+        mma_16816(d0, a[0], b[0].x, b[0].y);
+        mma_16816(d1, a[1], b[1].x, b[1].y);
+        mma_16816(d0, a[2], b[2].x, b[2].y);
+        mma_16816(d1, a[3], b[3].x, b[3].y);
+      }
+      return (((d0[0] + d1[0]) + (d0[2] + d1[2])) + ((d0[1] + d1[1]) + (d0[3] + d1[3]))) * gscale;
+    };
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int band = unit / p.groups;
       const int w0 = (unit - band * p.groups) * kBandWins;
-      if (band != cur_band) {                                  // this warp's contiguous run of the band's entries
+      if (band != cur_band) {                                  // this warp's position groups of the band: gw, gw + 20, ...
         cur_band = band;
-        const int s0 = p.band_start[band], b1 = p.band_start[band + 1];
-        const int per = (b1 - s0 + kWgWarps - 1) / kWgWarps;
-        e_begin = min(b1, s0 + gw * per);
-        cnt = min(b1, e_begin + per) - e_begin;
-        if (p.experiment & 32) cnt = 0;
-        fast = per <= kWgWarpCap;
+        g_first = p.band_gstart[band];
+        g_cnt = (p.experiment & 32) ? 0 : p.band_gstart[band + 1] - g_first;
+        fast = g_cnt <= kWgWarps * kWgGroupCap;
+        n_mine = 0;
 #pragma unroll
-        for (int i = 0; i < kWgWarpCap; ++i) rr[i] = (fast && i < cnt) ? p.ent_pos[e_begin + i] - band * kBandRows : 0;
+        for (int i = 0; i < kWgGroupCap; ++i) {
+          const int gi = gw + i * kWgWarps;
+          if (fast && gi < g_cnt) { const int2 m = p.grp[g_first + gi]; my_e0[i] = m.x; my_meta[i] = m.y; n_mine = i + 1; }
+        }
       }
-      // ---------------- gather: this warp's entries x the unit's 8 windows, one K-half per pass.  Few entries per warp
-      // (20 warps share the band's ~45) keep the time a K-half's regions are held short: the slab is single-buffered, so
-      // the next unit's loads start only when every consumer has released a region.
-      float c0[kWgWarpCap];                                    // pass-0 halves of the fast path (lanes with (lane & 3) == 0)
+      // ---------------- gather: this warp's position groups x the unit's 8 windows, one K-half per pass (the MMAs' order, so a
+      // K-half's two regions go back to the producer while the other K-half is still in use)
+      float c0[kWgGroupCap];                                   // pass-0 halves of the fast path
 #pragma unroll 1
       for (int kh = 0; kh < 2; ++kh) {
         int bh = b0 + 2 * kh; if (bh >= kWgBufs) bh -= kWgBufs;               // buffer of this K-half's hi16 region
         int bl = b0 + 2 * kh + 1; if (bl >= kWgBufs) bl -= kWgBufs;           // ... and of its lo16 region
         const uint32_t ph_h = (phases >> bh) & 1, ph_l = (phases >> bl) & 1;
         phases ^= (1u << bh) | (1u << bl);
-        const uint32_t reg_base = slab + (plane ? bl : bh) * kWgRegion + wodd * (kBandRows * 128) + (jch << 4);
+        const uint32_t hi_base = slab + bh * kWgRegion, lo_base = slab + bl * kWgRegion;
+        if (p.dbg) tq = clock64();
+        mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);          // hi16 K-half kh
+        mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);          // lo16 K-half kh
+        if (p.dbg) { const long long t = clock64(); c_wait_full += t - tq; tq = t; }
         if (fast) {
-          if (p.dbg) tq = clock64();
-          mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);          // hi16 K-half kh
-          mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);          // lo16 K-half kh
-          if (p.dbg) { const long long t = clock64(); c_wait_full += t - tq; tq = t; }
-          // Entries are sorted by position and 46 % of them share their row with a neighbour (8,400 entries hit ~4,500
-          // distinct positions): a row that the previous entry of this warp already pulled out of the slab is not read again.
-          // (Timing experiment 256 -- rows read, no arithmetic -- costs as much as the full gather: the LDS traffic next to the
-          // MMAs' operand reads and the TMA fills is what the gather costs, not its FMAs.)
-          uint4 v[4];
 #pragma unroll
-          for (int i = 0; i < kWgWarpCap; ++i)
-            if (i < cnt) {
-              if (i == 0 || rr[i] != rr[i - 1]) {
-                const uint32_t ad = (reg_base + rr[i] * 128) ^ ((rr[i] & 7) << 4);   // 128-byte swizzle: chunk j -> j ^ (row & 7)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = lds128(ad + j * (2 * kBandRows * 128));
-              }
-              // Folded weights of this entry and K-half through L1 / L2 (evict_last).  Staging them in shared memory instead
-              // (30 KB, private slots per warp) was measured and is slower (1.11 / 1.30 ms): the kernel's limit is the
-              // shared-memory port (UMMA operand reads 288 KB + TMA fills 131 KB + these LDS per unit ~ 95 of 128 B/cycle;
-              // cycle counters: ~650 cycles per (entry, K-half) in a consumer warp with everything in shared memory), so
-              // weight reads are better off on the L1 / L2 path.
-              const float* wp = p.ent_w + static_cast<size_t>(e_begin + i) * kC + kh * 64 + jch * 8;
-              const float4 wa = ldg_weights(wp), wb = ldg_weights(wp + 4);
-              float a[4];
-              if (p.experiment & 256) {                        // timing experiment: rows are read, no arithmetic
-                asm volatile("" :: "r"(v[0].x | v[1].x | v[2].x | v[3].x));
-                c0[i] = 0.f;
-                continue;
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) a[j] = dot8_h(v[j], wa, wb);
-              const float c = reduce4(a);
-              if (kh == 0) c0[i] = c;
-              else if ((lane & 3) == 0 && !(p.experiment & 64)) p.part_t[static_cast<size_t>(e_begin + i) * p.n_pad + w0 + wi_out] = c0[i] + c;
+          for (int i = 0; i < kWgGroupCap; ++i)
+            if (i < n_mine) {
+              const float v = gather_group(my_e0[i], my_meta[i], kh, hi_base, lo_base);
+              if (kh == 0) c0[i] = v;
+              else if (tig < (my_meta[i] >> 8) && !(p.experiment & 64))         // 8 lanes (gid = window) write 32 contiguous bytes
+                p.part_t[static_cast<size_t>(my_e0[i] + tig) * p.n_pad + w0 + gid] = c0[i] + v;
             }
         } else {
-          // generic path (band with more than 64 entries): pass-0 halves parked in part_t itself
-          mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);
-          mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);
+          // generic path (a band with more than 40 position groups: only patch sets that put more than 4 entries on many
+          // positions): pass-0 halves are parked in part_t itself (the same thread reads them back in pass 1)
 #pragma unroll 1
-          for (int i = 0; i < cnt; ++i) {
-            const int e = e_begin + i;
-            const int r = p.ent_pos[e] - band * kBandRows;
-            const float* wp = p.ent_w + static_cast<size_t>(e) * kC + kh * 64 + jch * 8;
-            const float4 wa = ldg_weights(wp), wb = ldg_weights(wp + 4);
-            const uint32_t ad = (reg_base + r * 128) ^ ((r & 7) << 4);
-            float a[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = dot8_h(lds128(ad + j * (2 * kBandRows * 128)), wa, wb);
-            const float c = reduce4(a);
-            if ((lane & 3) == 0) {
-              float* gp = p.part_t + static_cast<size_t>(e) * p.n_pad + w0 + wi_out;
-              *gp = kh == 0 ? c : *gp + c;
+          for (int gi = gw; gi < g_cnt; gi += kWgWarps) {
+            const int2 m = p.grp[g_first + gi];
+            const float v = gather_group(m.x, m.y, kh, hi_base, lo_base);
+            if (tig < (m.y >> 8)) {
+              float* gp = p.part_t + static_cast<size_t>(m.x + tig) * p.n_pad + w0 + gid;
+              *gp = kh == 0 ? v : *gp + v;
             }
           }
         }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&a_empty[bh]); mbar_arrive(&a_empty[bl]); }           // this warp is done with the K-half's regions
-        if (p.dbg && fast) c_gather += clock64() - tq;
+        if (p.dbg) c_gather += clock64() - tq;
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
-      // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g
+    }
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* d = p.dbg + blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = c_wait_full; d[2] = c_gather; d[5] = it;
+    }
+  } else if (warp >= 4 + kWgWarps) {
+    // ===================================================================== accumulator epilogue
+    const int ew = warp - 4 - kWgWarps;                        // 0..7
+    const int wq = warp & 3;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
+    const int eh = ew >> 2;                                    // pool groups eh and eh + 2 of the band
+    const int ch = wq * 32 + lane;
+    const float oscale = p.out_scale;
+    long long c_wait_acc = 0, c_epi = 0, tq = 0;
+    int it = 0;
+    for (int unit = u_begin; unit < u_end; ++unit, ++it) {
+      const int band = unit / p.groups;
+      const int w0 = (unit - band * p.groups) * kBandWins;
+      // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g.  Accumulator column
+      // n = 8 * (position inside the band) + window, so pool group g is columns 64 g .. 64 g + 63 and a thread (= channel) takes the
+      // maximum over the 8 registers with stride 8 that belong to one window.
       const int as = p.ts_mode ? 0 : (it & 1);
       const uint32_t accphase = p.ts_mode ? (it & 1) : ((it >> 1) & 1);
       if (p.dbg) tq = clock64();
       mbar_wait(&acc_full[as], accphase, p.status, 540 + as);
       if (p.dbg) { const long long t = clock64(); c_wait_acc += t - tq; tq = t; }
       tc_fence_after();
-      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256;
 #pragma unroll 1
-      for (int c32 = grp; c32 < kBandWins; c32 += kWgWarps / 4) {
-        const int w = w0 + c32;
-        if (w >= p.n_windows) break;                           // uniform: the rest of the unit is past the batch end
+      for (int g = eh; g < kBandRows / kPool; g += 2) {
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256 + g * (kPool * kBandWins);
+        float m[kBandWins];
         uint32_t r[32];
-        tmem_ld_32x32(lane_addr + c32 * 32, r);
+        tmem_ld_32x32(lane_addr, r);                           // positions 0..3 of the pool group x 8 windows
         tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float m = __uint_as_float(r[8 * g]);
+        for (int w = 0; w < kBandWins; ++w)
+          m[w] = fmaxf(fmaxf(__uint_as_float(r[w]), __uint_as_float(r[8 + w])), fmaxf(__uint_as_float(r[16 + w]), __uint_as_float(r[24 + w])));
+        tmem_ld_32x32(lane_addr + 32, r);                      // positions 4..7
+        tmem_wait_ld();
 #pragma unroll
-          for (int k = 1; k < 8; ++k) m = fmaxf(m, __uint_as_float(r[8 * g + k]));
-          const int gg = band * (kBandRows / kPool) + g;
-          if (gg < kPooled && !(p.experiment & 128)) p.q_out[(static_cast<size_t>(w) * kPooled + gg) * kC + ch] = m * oscale;
+        for (int w = 0; w < kBandWins; ++w)
+          m[w] = fmaxf(m[w], fmaxf(fmaxf(__uint_as_float(r[w]), __uint_as_float(r[8 + w])), fmaxf(__uint_as_float(r[16 + w]), __uint_as_float(r[24 + w]))));
+        const int gg = band * (kBandRows / kPool) + g;
+        if (gg < kPooled && !(p.experiment & 128)) {
+#pragma unroll
+          for (int w = 0; w < kBandWins; ++w)
+            if (w0 + w < p.n_windows) p.q_out[(static_cast<size_t>(w0 + w) * kPooled + gg) * kC + ch] = m[w] * oscale;
         }
       }
       tc_fence_before();
@@ -402,9 +406,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (p.dbg) c_epi += clock64() - tq;
     }
-    if (p.dbg && warp == 4 && lane == 0) {
+    if (p.dbg && ew == 0 && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 8;
-      d[0] = clock64() - t_begin; d[1] = c_wait_full; d[2] = c_gather; d[3] = c_wait_acc; d[4] = c_epi; d[5] = it;
+      d[3] = c_wait_acc; d[4] = c_epi;
     }
   }
 

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--steps-per-call", type=int, default=1, help="internal steps per API call (> 1 exercises the tail overlap)")
     ap.add_argument("--wvg-cycles", action="store_true", help="print the fused IGLOO kernel's per-CTA cycle breakdown (conv_experiment bit 512)")
+    ap.add_argument("--wvg-exp", type=int, nargs="*", default=[0], help="timing-experiment bits to add to the cycle-counter runs (32 = no gather, 256 = gather reads only)")
     args = ap.parse_args()
     B = args.batch
     clf = engine.Classifier(None, device=0, max_batch=B)
@@ -81,18 +82,19 @@ def main():
                     print(f"    max |dp| vs first configuration: {(pr - base).abs().max().item():.2e}", flush=True)
     if args.wvg_cycles:
         clf.set_option("fuse_gather", 1)
-        wvg_cycles(clf, pool)
+        for bits in args.wvg_exp:
+            wvg_cycles(clf, pool, bits)
 
 
-def wvg_cycles(clf, pool):
-    names = ["consumer total", "consumer wait a_full", "consumer gather (LDS + math + release)", "consumer wait acc_full",
-             "consumer epilogue", "units", "MMA wait a_full", "MMA wait acc_empty"]
-    clf.set_option("conv_experiment", 512)
+def wvg_cycles(clf, pool, bits=0):
+    names = ["gather warp total", "gather warp wait a_full", "gather warp gather (reads + mma + release)", "epilogue warp wait acc_full",
+             "epilogue warp epilogue", "units", "MMA wait a_full", "MMA wait acc_empty"]
+    clf.set_option("conv_experiment", 512 | bits)
     clf.predict_ascii(pool[0]); torch.cuda.synchronize()
     d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
     clf.set_option("conv_experiment", 0)
     units = max(d[:, 5].mean(), 1)
-    print("wv_gather_kernel (IGLOO#1) cycle breakdown, mean over CTAs (warp 4 = one consumer warp; warp 1 = MMA issuer):")
+    print(f"wv_gather_kernel (IGLOO#1) cycle breakdown, experiment bits {bits}, mean over CTAs (warp 4 = a gather warp, warp 16 = an epilogue warp, warp 1 = MMA issuer):")
     for i, nm in enumerate(names):
         print(f"   {nm:42s} {d[:, i].mean():12.0f}   per unit {d[:, i].mean() / units:9.0f}   (min {d[:, i].min():.0f}, max {d[:, i].max():.0f})")
 
