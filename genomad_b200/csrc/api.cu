@@ -55,7 +55,6 @@ struct gnm_handle {
   int debug_stop = 0;       // 0 = full pipeline; 1 = stop after embed+gather0; 2 = after conv2; 3 = after conv3
   int profile_stages = 0;
   int conv_experiment = 0;
-  int wv_tmem_a = 0;        // experiment: fused IGLOO kernel reads its w_v weights (A operand) from tensor memory
   uint32_t* wv_t16[2] = {nullptr, nullptr};          // [2 hi/lo][128 cout][64 packed fp16 pairs along k] of w_v^T
   int conv_cluster = 1;     // experiment: thread-block cluster size of the conv kernel's launch (1 = no clusters)
   int fuse_gather = 1;      // 1 = w_v + patch gather in one pass over the activations (wv_gather.cuh); 0 = conv_t_kernel<true> + patch_stream_kernel
@@ -88,7 +87,7 @@ struct gnm_handle {
   CUtensorMap tm_lg_b[2][2];                         // [igloo][hi/lo] over wqkT_hi / wqkT_lo
   float* part = nullptr;                             // [max_batch][kGsSlots] per-entry partial dot products ([kGsSlots][mb_pad] in the fused path)
   int2* grp[2] = {nullptr, nullptr};                 // wv_gather_kernel: position groups {first entry slot, row in band | entries << 8}
-  int32_t* band_gstart[2] = {nullptr, nullptr};      // [kNumBands + 1] first position group of every 32-position band
+  int32_t* band_gstart[2] = {nullptr, nullptr};      // [kNumBands + 1] first position group of every band
   uint4* wfrag[2] = {nullptr, nullptr};              // [kGsSlots][2][4][4] folded weights as mma.m16n8k16 B fragments (fp16 hi / lo halves)
   float gather_unscale[2] = {1.f, 1.f};              // 1 / the power of two applied to the folded weights before the fp16 split
   std::vector<int32_t> band_groups[2];               // host copy: position groups per band (cost model of wv_gather_kernel's unit split)
@@ -97,7 +96,7 @@ struct gnm_handle {
   int split_groups[2] = {-1, -1}, split_grid[2] = {-1, -1};
   float wv_cost_base = 1.f, wv_cost_group = 0.1f;    // unit cost model of wv_split: base + per position group of the busiest warp
   int mb_pad = 0;                                    // max_batch rounded up to a multiple of 8 (window groups of wv_gather_kernel)
-  CUtensorMap tm_band[2];                            // activations, box = 128 B x 8 windows x 32 positions (make_band_map)
+  CUtensorMap tm_band[2];                            // activations, box = 128 B x 8 windows x 24 positions (make_band_map)
   float* logits = nullptr; float* logits_part = nullptr; float* h0 = nullptr; float* h1 = nullptr; float* h2 = nullptr;
   float* scratch32 = nullptr;                        // validation path only, allocated lazily
   uint8_t* in_stage[2] = {nullptr, nullptr};         // gnm_classify_host
@@ -164,8 +163,8 @@ static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int
   return 0;
 }
 // wv_gather_kernel's view of the activations: the WINDOW axis is listed before the POSITION axis (strides need not ascend), so
-// the box {128 B, 8 windows, 32 positions} lands in shared memory as [position][window][128 B]: the 8 windows of one position are
-// one 1024-byte swizzle atom -- what the gather's ldmatrix wants -- and the 256 rows are still one K-major N = 256 UMMA operand.
+// the box {128 B, 8 windows, 24 positions} lands in shared memory as [position][window][128 B]: the 8 windows of one position are
+// one 1024-byte swizzle atom -- what the gather's ldmatrix wants -- and the 192 rows are still one K-major N = 192 UMMA operand.
 // Checked on B200 incl. the zero fill of positions >= 5997: tools/tma_order_probe.cu.
 static int make_band_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows) {
   cuuint64_t dims[3] = {kRowBytes, static_cast<cuuint64_t>(n_windows), kTok};
@@ -657,11 +656,11 @@ static int launch_wv_gather(gnm_handle* h, int s, int buf, int n, cudaStream_t s
   p.status = h->status;
   p.experiment = h->conv_experiment;
   p.dbg = (h->conv_experiment & 512) && s == 1 ? h->conv_dbg : nullptr;      // cycle counters of the IGLOO#1 launch
-  p.wv_t16 = h->wv_t16[s]; p.ts_mode = h->wv_tmem_a;
+  p.wv_t16 = h->wv_t16[s];
   const int grid = std::min(h->num_sms, p.n_units);
   if (wv_split(h, s, p.groups, grid, st)) return 1;
   p.cta_split = h->cta_split + s * (h->num_sms + 1);
-  wv_gather_kernel<<<grid, kWgThreads, kWgSmem, st>>>(h->tm_band[buf], h->tm_w[2 + s], p);
+  wv_gather_kernel<<<grid, kWgThreads, kWgSmem, st>>>(h->tm_band[buf], p);
   if (check_launch(h, "wv_gather_kernel")) return 1;
   dim3 fgrid((kPatches + 31) / 32, (n + 31) / 32);
   patch_finish_t_kernel<<<fgrid, 256, 0, st>>>(h->part, h->slot_of[s], h->wbias[s], h->mpi[s], h->mpi_hi[s], h->mpi_lo[s], n, p.n_pad);
@@ -1049,7 +1048,6 @@ extern "C" int gnm_set_option(gnm_handle* h, const char* name, int value) {
   else if (k == "fuse_l1") h->fuse_l1 = value ? 1 : 0;
   else if (k == "fuse_gather") h->fuse_gather = value ? 1 : 0;
   else if (k == "tail_overlap") h->tail_overlap = value ? 1 : 0;
-  else if (k == "wv_tmem_a") h->wv_tmem_a = value ? 1 : 0;
   else if (k == "wv_cost_group") {      // experiment: per-mille cost of one position group per warp in wv_split's unit cost model (base = 1000)
     if (value < 0 || value > 10000) return fail("wv_cost_group must be in [0, 10000]");
     h->wv_cost_group = value * 1e-3f; h->split_groups[0] = h->split_groups[1] = -1;

@@ -6,37 +6,45 @@
 //   mpi   = gather_nd(transpose(y), patches) * w_mult, reshaped, @ w_summer + w_bias          (lines 192-206)
 //   y_proj = y @ w_v, MaxPool1D(8)                                                              (lines 208-210)
 //
-// Work decomposition: POSITION BANDS.  A unit is one band of 32 consecutive positions of 8 consecutive windows
-// (256 activation rows = one N = 256 tensor-core tile; 188 bands x ceil(n/8) window groups).  Units are numbered
+// Work decomposition: POSITION BANDS.  A unit is one band of 24 consecutive positions of 8 consecutive windows
+// (192 activation rows = one N = 192 tensor-core tile; 250 bands x ceil(n/8) window groups).  Units are numbered
 // band-major and every CTA owns a contiguous range of them, so a CTA stays on one band (at most three) for the whole
 // launch while the grid as a whole sweeps the windows front to back.  That is what makes the gather cheap here: the
-// ~45 (patch, slot) entries whose position falls into the CTA's band use the same 23 KB of folded weights for every unit
+// ~34 (patch, slot) entries whose position falls into the CTA's band use the same 17 KB of folded weights for every unit
 // (L1 / L2 resident), instead of every window re-reading all 4.3 MB.
 //
-//   * value projection: as conv_t_kernel<true> (3 fp16 passes Ahi*Whi + Alo*Whi + Ahi*Wlo into one TMEM accumulator,
-//     operands swapped so that D^T[cout][row]), but the four slab regions [8 windows][32 rows][128 B] come from ONE 3-D TMA
-//     box each, and the 64 KB of w_v weight stages stay resident in shared memory for the whole launch (the old kernel
-//     re-streamed them for every unit: a third of its L2 -> SM traffic).
-//   * patch gather: the 20 consumer warps that drain the accumulators first run the band's entries (<= 3 per warp) against the
-//     unit's 8 windows, reading the rows from the SLAB IN SHARED MEMORY that the TMA engine filled for the MMAs.  The gather
-//     follows the MMAs' K-half order so slab regions are still recycled one K-half at a time: pass 0 takes channels 0..63 from
-//     the hi16.k0 / lo16.k0 regions, pass 1 channels 64..127 from hi16.k1 / lo16.k1; a region goes back to the producer when
-//     both the tensor core (tcgen05.commit) and every consumer warp have arrived on its "empty" barrier (count 21).
-//     One LDS.128 per lane covers two windows of one entry: lanes 0-7 / 8-15 read the 128-byte hi / lo row of window 2i
-//     (16-byte chunk j of a row sits at chunk j ^ (row & 7): TMA's 128-byte swizzle), lanes 16-31 the same for window 2i+1;
-//     each quarter-warp reads one whole row, so the access is bank-conflict free.  A row that the warp's previous entry
-//     already pulled out is not read again (entries are sorted by position; 46 % share their row with a neighbour).  The four
-//     partial sums per lane are reduced by a 5-shuffle transposing butterfly (fixed order -> deterministic); lanes
-//     0,4,..,28 end up with the 8 windows' values and write part_t[slot][window] after pass 1 (the pass-0 halves wait in
-//     registers; bands with more than 60 entries take a generic path that parks them in part_t).
-//     patch_finish_t_kernel adds a patch's four slots in fixed order k = 0..3 plus the bias, as before.
-//   * what bounds it (profiles/r02_wv_gather_ncu.md): not HBM (48 % of peak) and not the gather's FMAs -- reading
-//     the rows WITHOUT any arithmetic costs the same -- but the shared-memory port that UMMA operand reads (288 KB per unit),
-//     TMA fills (131 KB) and the gather's LDS (~150 KB) share: ~650 cycles per (entry, K-half) in a consumer warp.
+// Slab.  The four regions of a unit (hi16 / lo16 plane x channel half) are ONE 3-D TMA box each, from a tensor map that lists
+// the window axis BEFORE the position axis (api.cu make_band_map; tools/tma_order_probe.cu): the box {128 B, 8 windows, 24
+// positions} lands as [position][window][128 B], i.e. the 8 windows of one position are one 1024-byte swizzle atom.  For the
+// tensor core the region is still a plain K-major SWIZZLE_128B operand of 192 rows (accumulator column n = 8 * position +
+// window); for the gather it means "one position x 8 windows" is one conflict-free ldmatrix.  Eight region buffers = two units
+// in flight: the TMA producer fills unit u+1 while the MMAs and the gather work on unit u (with one unit of buffering every
+// role waited on the same load -> use -> release chain: 7.1 k cycles per 256 rows; now 4.8 k per 192).
 //
-// Warp roles (768 threads, 1 CTA per SM):  warp 0 lane 0: weight loader (once) | warp 1: tcgen05.mma issuer |
-// warp 2: TMEM allocator | warp 3 lane 0: activation producer (TMA) | warps 4..23: patch gather, then epilogue
-// (max over 8 positions = max over 8 registers; a warp writes 128 contiguous bytes of q[g][:] per pooled row).
+//   * value projection: 3 fp16 passes Ahi*Whi + Alo*Whi + Ahi*Wlo into one TMEM accumulator, operands swapped so that
+//     D^T[cout][row].  The w_v weights are the A operand and live in TENSOR MEMORY (tcgen05.mma TS form; copied there once per
+//     CTA with tcgen05.st): no shared memory for them (that is what pays for the second unit of buffering) and a third fewer
+//     operand bytes through the shared-memory port.  TMEM: 2 accumulators x 192 columns + 128 columns of weights = 512.
+//   * patch gather: warp-level mma.sync.m16n8k16 on the slab rows.  Entries are grouped by position (<= 4 per group;
+//     8,400 entries hit ~4,500 positions).  For one group and one channel half, A[16 x 64] = the position's 8 windows' hi16 rows
+//     (rows 0-7) and lo16 rows (rows 8-15), read by 4 ldmatrix.x4; B[64 x 8] = the fp16 hi / lo halves of the group's folded
+//     weights (host-packed in fragment order, scaled by a power of two so the lo halves stay normal; L1 / L2 resident); the sum of
+//     the four D entries of (window, entry) is (hi + lo) . (w_hi + w_lo) with fp32 accumulation -- the fp32-equivalent dot product
+//     (tools/tma_order_probe.cu: 8e-8 absolute on O(1) sums).  16 gather warps take <= 2 groups each; pass 0 (channels 0-63) waits
+//     in registers, pass 1 adds channels 64-127 and writes part_t[slot][window] (8 lanes = 32 contiguous bytes).  A K-half's two
+//     regions go back to the producer when the tensor core (tcgen05.commit) and all 16 gather warps have arrived (count 17).
+//     patch_finish_t_kernel adds a patch's four slots in fixed order k = 0..3 plus the bias, as before.
+//   * epilogue: 4 warps (one per TMEM lane quarter) read the accumulator; pool group g of the band is columns 64 g .. 64 g + 63, a
+//     thread (= channel) takes the maximum over the 8 registers of one window and a warp writes 128 contiguous bytes of q.
+//   * what bounds it now (cycle counters of tools/ab_stages.py --wvg-cycles): the gather warps, and inside them the
+//     warp-level mma: it shares the tensor pipe with the tcgen05.mma stream and waits ~190 cycles per instruction (gather phase
+//     3.4 k cycles per unit; 2.1 k with the mma switched off, 3.2 k with the loads switched off).  Splitting every tcgen05.mma
+//     into two N = 96 slices (more instruction boundaries) changes nothing; neither do four independent accumulators.
+//     Earlier forms of this kernel (FFMA gather from a window-major slab, 20 merged gather + epilogue warps, weights in shared
+//     memory, one unit of buffering) are in DESIGN.md 5.1 with their numbers.
+//
+// Warp roles (768 threads, 1 CTA per SM):  warp 1: tcgen05.mma issuer | warp 2: TMEM allocator | warp 3 lane 0: activation
+// producer (TMA) | warps 4..19: patch gather (warps 4..7 first copy the weights into tensor memory) | warps 20..23: epilogue.
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -46,26 +54,32 @@
 
 namespace gnm {
 
-constexpr int kBandRows   = 32;                                   // positions per band (multiple of the pool size 8)
+constexpr int kBandRows   = 24;                                   // positions per band (multiple of the pool size 8)
 constexpr int kBandWins   = 8;                                    // windows per unit
-constexpr int kNumBands   = (kTok + kBandRows - 1) / kBandRows;   // 188 (the last band holds 13 valid rows)
-constexpr int kWgRegion   = kBandRows * kBandWins * 128;          // bytes per slab region (256 rows x 128 B) = 32768
-constexpr int kWgBufs     = 4;                                    // region buffers.  The code is a ring (region k of unit `it` lives in buffer
-                                                                  // (4 it + k) % kWgBufs): with 5 buffers the TMA can run one region ahead of
-                                                                  // the consumers' releases -- measured, no gain (1.15 / 1.26 ms vs 1.05 / 1.14),
-                                                                  // so the slab stays at exactly one unit
-constexpr int kWgSlab     = kWgBufs * kWgRegion;                  // hi16.k0 | lo16.k0 | hi16.k1 | lo16.k1        = 131072
-constexpr int kWgWeights  = kWvStages * kBStage;                  // resident w_v stages                         =  65536
-constexpr int kWgWarps    = 12;                                   // patch-gather warps
-constexpr int kWgEpiWarps = 8;                                    // accumulator-epilogue warps (two per TMEM lane quarter)
+constexpr int kWgN        = kBandRows * kBandWins;                // activation rows per unit = N of the unit's tcgen05.mma (192)
+constexpr int kNumBands   = (kTok + kBandRows - 1) / kBandRows;   // 250 (the last band holds 21 valid rows)
+constexpr int kWgRegion   = kWgN * 128;                           // bytes per slab region (192 rows x 128 B)               =  24576
+constexpr int kWgBufs     = 8;                                    // region buffers = TWO units in flight: region k of unit `it` lives in buffer
+                                                                  // (4 it + k) % 8, so the TMA fills the next unit while this one is in use
+constexpr int kWgSlab     = kWgBufs * kWgRegion;                  //                                                        = 196608
+constexpr int kWgWarps    = 16;                                   // patch-gather warps
+constexpr int kWgEpiWarps = 4;                                    // accumulator-epilogue warps (one per TMEM lane quarter)
 constexpr int kWgThreads  = (4 + kWgWarps + kWgEpiWarps) * 32;    // 768
-constexpr int kWgGroupCap = 3;                                    // position groups per warp on the fast path (36 per band; a band has <= 32
+constexpr int kWgGroupCap = 2;                                    // position groups per warp on the fast path (32 per band; a band has <= 24
                                                                   // positions, so only positions with more than 4 entries can exceed it)
 constexpr int kWgGroupMax = 4;                                    // entries per position group: the 8 columns of mma.m16n8k16 = 4 entries x (hi, lo)
-constexpr int kWgSmem     = kWgSlab + kWgWeights + 2048;          //                                                   = 198656
+constexpr int kWgSmem     = kWgSlab + 2048;                       //                                                        = 198656
+// tensor memory (512 columns): two accumulators of kWgN columns, then the w_v weights (A operand of the TS-form tcgen05.mma):
+// fp16 pairs along k, 64 columns for the hi halves and 64 for the lo halves
+constexpr int kWgTmemW    = 2 * kWgN;                             // 384
+constexpr int kWgMmaSplit = 1;                                    // every tcgen05.mma of a unit is issued as this many column slices (N = 96): the gather's
+                                                                  // warp-level mma only gets the tensor pipe between two tcgen05.mma
+static_assert((kWgN / kWgMmaSplit) % 16 == 0 && ((kWgN / kWgMmaSplit) * 128) % 1024 == 0, "slices must be valid N and start on a swizzle atom");
+static_assert(kWgTmemW + 128 <= 512, "two accumulators + the weights must fit the 512 TMEM columns");
 static_assert(kWgSmem <= 232448, "wv_gather_kernel exceeds the 227 KB of shared memory a CTA may use");
-static_assert(kWgWarps % 4 == 0 && kWgEpiWarps == 8 && kBandRows / kPool == 4, "epilogue warp (quarter wq, half eh) takes pool groups eh and eh + 2");
-static_assert(kBandRows * kBandWins == 256, "one unit = one N = 256 tile");
+static_assert(kWgN % 16 == 0 && kWgN <= 256 && kBandRows % kPool == 0 && kBandRows <= 32, "unit shape");
+static_assert(kWgRegion % 1024 == 0, "regions must keep the 1024-byte alignment of the 128-byte swizzle");
+static_assert(kWgEpiWarps == 4 && kWgWarps % 4 == 0 && kWgWarps >= 4, "one epilogue warp per TMEM lane quarter; the first four gather warps load the weights");
 
 struct WvGatherParams {
   float* q_out;                // [n][749][128]
@@ -80,8 +94,7 @@ struct WvGatherParams {
   int n_units;                 // kNumBands * groups
   const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
   int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows and weights but does no arithmetic, 1024 = no weight loads, 2048 = no ldmatrix
-  const uint32_t* wv_t16;      // [2 hi/lo][128 cout][64] packed fp16 pairs of w_v^T (A operand from tensor memory, ts_mode)
-  int ts_mode;                 // 1 = w_v weights live in TMEM (columns 256..383), one accumulator; 0 = weights in shared memory, two accumulators
+  const uint32_t* wv_t16;      // [2 hi/lo][128 cout][64] packed fp16 pairs of w_v^T: the A operand, copied into tensor memory once per CTA
   long long* dbg;              // optional [gridDim.x][8] cycle counters (nullptr = off), see tools/ab_stages.py --wvg-cycles
   DeviceStatus* status;
 };
@@ -103,20 +116,18 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
-wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_constant__ CUtensorMap tm_w,
-                 const WvGatherParams p) {
-  constexpr uint32_t kIdesc = umma_idesc_f16(128, 256);
+wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const WvGatherParams p) {
+  constexpr uint32_t kIdesc = umma_idesc_f16(128, kWgN / kWgMmaSplit);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_a = smem;                                   // ring of kWgBufs region buffers, each [8 windows][32 rows] x 128 B
-  uint8_t* s_w = smem + kWgSlab;                         // 4 resident weight stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + kWgWeights);
-  uint64_t* a_full = bars;            // [kWgBufs <= 5]  per buffer
-  uint64_t* a_empty = bars + 5;       // [kWgBufs <= 5]
-  uint64_t* w_full = bars + 10;       // [1]
-  uint64_t* acc_full = bars + 11;     // [2]
-  uint64_t* acc_empty = bars + 13;    // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 15);
+  uint8_t* s_a = smem;                                   // ring of kWgBufs region buffers, each [24 positions][8 windows] x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgSlab);
+  uint64_t* a_full = bars;            // [kWgBufs = 8]  per buffer
+  uint64_t* a_empty = bars + 8;       // [kWgBufs = 8]
+  uint64_t* w_full = bars + 16;       // [1]
+  uint64_t* acc_full = bars + 17;     // [2]
+  uint64_t* acc_empty = bars + 19;    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 21);
   // Region k of a unit (need order: 0 hi16.k0, 1 lo16.k0, 2 hi16.k1, 3 lo16.k1) is load number g = 4 * it + k of this CTA and
   // lives in buffer g % kWgBufs; every role walks the buffers in the same order, so each keeps the first buffer of the
   // current unit (b0, advanced by 4 mod kWgBufs per unit) and one phase bit per buffer that it flips after each use.
@@ -127,9 +138,8 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_band);
-    tma_prefetch_desc(&tm_w);
     for (int i = 0; i < kWgBufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1 + kWgWarps); }    // tcgen05.commit + the gather warps
-    mbar_init(w_full, p.ts_mode ? 4 : 1);
+    mbar_init(w_full, 4);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kWgEpiWarps); }
     fence_barrier_init();
   }
@@ -142,9 +152,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (p.ts_mode && warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 8) {
     // ===================================================================== weights -> tensor memory (once): thread = output
-    // channel (TMEM lane), columns 256..319 = fp16(w_v^T) hi as 64 packed pairs along k, 320..383 = lo
+    // channel (TMEM lane), columns kWgTmemW .. +63 = fp16(w_v^T) hi as 64 packed pairs along k, the next 64 = lo
     const int cout = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 #pragma unroll 1
@@ -156,21 +166,14 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         const uint4 v = *reinterpret_cast<const uint4*>(src + i);
         r[i] = v.x; r[i + 1] = v.y; r[i + 2] = v.z; r[i + 3] = v.w;
       }
-      tmem_st_32x32(lane_addr + 256 + part * 32, r);
+      tmem_st_32x32(lane_addr + kWgTmemW + part * 32, r);
     }
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(w_full);
   }
-  if (warp == 0 && lane == 0) {
-    // ===================================================================== weights: loaded once, resident
-    if (!p.ts_mode) {
-      const uint64_t pol = l2_policy_evict_last();
-      mbar_arrive_expect_tx(w_full, kWgWeights);
-      for (int q = 0; q < kWvStages; ++q) tma_load_2d_hint(s_w + q * kBStage, &tm_w, w_full, 0, q * 128, pol);
-    }
-  } else if (warp == 3 && lane == 0) {
+  if (warp == 3 && lane == 0) {
     // ===================================================================== activation producer
     const uint64_t pol = l2_policy_evict_first();
     uint32_t phases = 0;                                   // bit b: parity of buffer b's next "empty" wait is phase ^ 1
@@ -194,18 +197,16 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     // ===================================================================== MMA issuer (converged warp, elected lane issues)
     const uint64_t desc0 = umma_desc_sw128(0);
     const uint32_t a_base = smem_u32(s_a);
-    const uint32_t w_base = smem_u32(s_w);
-    mbar_wait(w_full, 0, p.status, 510);
+    mbar_wait(w_full, 0, p.status, 510);                      // the weights are in tensor memory
     tc_fence_after();
-    const bool ts = p.ts_mode != 0;
     int it = 0;
     uint32_t phases = 0;
     int b0 = 0;
     long long m_wait_full = 0, m_wait_acc = 0, tq = 0;
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
-      const int as = ts ? 0 : (it & 1);                      // ts_mode: the second accumulator's columns hold the weights
-      const uint32_t accphase = ts ? (it & 1) : ((it >> 1) & 1);
-      const uint32_t acc = tmem_base + as * 256;
+      const int as = it & 1;
+      const uint32_t accphase = (it >> 1) & 1;
+      const uint32_t acc = tmem_base + as * kWgN;
       if (p.dbg) tq = clock64();
       mbar_wait(&acc_empty[as], accphase ^ 1, p.status, 520 + as);
       if (p.dbg) m_wait_acc += clock64() - tq;
@@ -218,30 +219,24 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         if ((q & 1) == 0) {
           if (p.dbg) tq = clock64();
           mbar_wait(&a_full[bh], (phases >> bh) & 1, p.status, 530 + bh);
-          mbar_wait(&a_full[bl], (phases >> bl) & 1, p.status, 536 + bl);
+          mbar_wait(&a_full[bl], (phases >> bl) & 1, p.status, 540 + bl);
           if (p.dbg) m_wait_full += clock64() - tq;
           phases ^= (1u << bh) | (1u << bl);
         }
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t wdesc = desc0 + ((w_base + q * kBStage) >> 4);                      // A: weights
           const uint64_t y0 = desc0 + ((a_base + bh * kWgRegion) >> 4);                      // B: hi16 rows
           const uint64_t y1 = desc0 + ((a_base + bl * kWgRegion) >> 4);                      // B: lo16 rows
           const bool w_lo = (q & 1) != 0;
-          if (ts) {
-            const uint32_t wt = tmem_base + 256 + (w_lo ? 64 : 0) + kh * 32;                 // 16 k-elements = 8 columns per MMA
+          const uint32_t wt = tmem_base + kWgTmemW + (w_lo ? 64 : 0) + kh * 32;              // A: 16 k-elements = 8 columns per MMA
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              umma_f16_ts(acc, wt + kk * 8, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
-              if (!w_lo) umma_f16_ts(acc, wt + kk * 8, y1 + kk * 2, kIdesc, 1u);
-            }
-          } else {
+          for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              umma_f16(acc, wdesc + kk * 2, y0 + kk * 2, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
-              if (!w_lo) umma_f16(acc, wdesc + kk * 2, y1 + kk * 2, kIdesc, 1u);
+            for (int hs = 0; hs < kWgMmaSplit; ++hs) {           // column slice hs of the unit: rows hs * kWgN / split .. of the regions
+              constexpr uint32_t kSliceDesc = (kWgN / kWgMmaSplit) * 128 >> 4;
+              umma_f16_ts(acc + hs * (kWgN / kWgMmaSplit), wt + kk * 8, y0 + kk * 2 + hs * kSliceDesc, kIdesc, (q == 0 && kk == 0) ? 0u : 1u);
+              if (!w_lo) umma_f16_ts(acc + hs * (kWgN / kWgMmaSplit), wt + kk * 8, y1 + kk * 2 + hs * kSliceDesc, kIdesc, 1u);
             }
-          }
           if (!w_lo) umma_commit(&a_empty[bl]);                  // the lo16 region is only used by the hi-weight stage
           else umma_commit(&a_empty[bh]);
           if (q == 3) umma_commit(&acc_full[as]);
@@ -253,7 +248,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 6] = m_wait_full; p.dbg[blockIdx.x * 8 + 7] = m_wait_acc; }
   } else if (warp >= 4 && warp < 4 + kWgWarps) {
     // ===================================================================== patch gather
-    const int gw = warp - 4;                                   // 0..11
+    const int gw = warp - 4;                                   // 0..15
     const float gscale = p.gather_unscale;
     // Gather lane roles.  ldmatrix: lanes 8i..8i+7 address matrix i = (plane i & 1: 0 hi16 / 1 lo16, 16-byte chunk i >> 1 of the
     // k-step), row lane & 7 = window.  The A fragment then holds rows 0..7 = the 8 windows' hi16 halves and rows 8..15 = their
@@ -267,9 +262,9 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     long long c_wait_full = 0, c_gather = 0, tq = 0;
     const long long t_begin = clock64();
     int cur_band = -1, g_first = 0, g_cnt = 0, n_mine = 0;
-    int my_e0[kWgGroupCap] = {0, 0, 0}, my_meta[kWgGroupCap] = {0, 0, 0};     // this warp's position groups of the band, fast path
+    int my_e0[kWgGroupCap] = {0, 0}, my_meta[kWgGroupCap] = {0, 0};     // this warp's position groups of the band, fast path
     bool fast = true;
-    // One position group x one K-half: D[16 x 8] = A[16 x 64] * B[64 x 8] as 4 k-steps (two independent chains of 2 mma).  B's
+    // One position group x one K-half: D[16 x 8] = A[16 x 64] * B[64 x 8] as 4 independent k-steps.  B's
     // columns are (entry 0 hi, entry 0 lo, entry 1 hi, ...): the fp16 hi / lo halves of up to 4 entries' folded weights.  Returns
     // entry tig of window gid: (hi16 row + lo16 row) x (hi-weight column + lo-weight column).
     auto gather_group = [&](int e0, int meta, int kh, uint32_t hi_base, uint32_t lo_base) -> float {
@@ -285,17 +280,22 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         if (p.experiment & 2048) { a[ks][0] = a[ks][1] = a[ks][2] = a[ks][3] = rb; continue; }
         ldsm_x4(rb + (((ks * 2 + lm_chunk) ^ lm_win) << 4), a[ks]);     // 128-byte swizzle: chunk j -> j ^ (row & 7)
       }
-      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+      // four independent accumulators: the warp-level mma shares the tensor pipe with the tcgen05.mma stream and waits long for its
+      // turn, so no mma of a group depends on another one
+      float d[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) d[ks][0] = d[ks][1] = d[ks][2] = d[ks][3] = 0.f;
       if (p.experiment & 256) {                              // timing experiment: rows and weights are read, no arithmetic
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) asm volatile("" :: "r"(a[ks][0] | a[ks][1] | a[ks][2] | a[ks][3] | b[ks].x | b[ks].y));
       } else {
-        mma_16816(d0, a[0], b[0].x, b[0].y);
-        mma_16816(d1, a[1], b[1].x, b[1].y);
-        mma_16816(d0, a[2], b[2].x, b[2].y);
-        mma_16816(d1, a[3], b[3].x, b[3].y);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_16816(d[ks], a[ks], b[ks].x, b[ks].y);
       }
-      return (((d0[0] + d1[0]) + (d0[2] + d1[2])) + ((d0[1] + d1[1]) + (d0[3] + d1[3]))) * gscale;
+      float v = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) v += (d[ks][0] + d[ks][2]) + (d[ks][1] + d[ks][3]);      // fixed order
+      return v * gscale;
     };
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int band = unit / p.groups;
@@ -324,7 +324,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
         const uint32_t hi_base = slab + bh * kWgRegion, lo_base = slab + bl * kWgRegion;
         if (p.dbg) tq = clock64();
         mbar_wait(&a_full[bh], ph_h, p.status, 550 + bh);          // hi16 K-half kh
-        mbar_wait(&a_full[bl], ph_l, p.status, 556 + bl);          // lo16 K-half kh
+        mbar_wait(&a_full[bl], ph_l, p.status, 560 + bl);          // lo16 K-half kh
         if (p.dbg) { const long long t = clock64(); c_wait_full += t - tq; tq = t; }
         if (fast) {
 #pragma unroll
@@ -360,9 +360,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     }
   } else if (warp >= 4 + kWgWarps) {
     // ===================================================================== accumulator epilogue
-    const int ew = warp - 4 - kWgWarps;                        // 0..7
     const int wq = warp & 3;                                   // TMEM lane quarter = channels 32*wq .. 32*wq+31
-    const int eh = ew >> 2;                                    // pool groups eh and eh + 2 of the band
     const int ch = wq * 32 + lane;
     const float oscale = p.out_scale;
     long long c_wait_acc = 0, c_epi = 0, tq = 0;
@@ -370,30 +368,29 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
     for (int unit = u_begin; unit < u_end; ++unit, ++it) {
       const int band = unit / p.groups;
       const int w0 = (unit - band * p.groups) * kBandWins;
-      // ---------------- epilogue: q[w][band*4 + g][ch] = max over the 8 positions of pool group g.  Accumulator column
+      // ---------------- epilogue: q[w][band*3 + g][ch] = max over the 8 positions of pool group g.  Accumulator column
       // n = 8 * (position inside the band) + window, so pool group g is columns 64 g .. 64 g + 63 and a thread (= channel) takes the
       // maximum over the 8 registers with stride 8 that belong to one window.
-      const int as = p.ts_mode ? 0 : (it & 1);
-      const uint32_t accphase = p.ts_mode ? (it & 1) : ((it >> 1) & 1);
+      const int as = it & 1;
+      const uint32_t accphase = (it >> 1) & 1;
       if (p.dbg) tq = clock64();
-      mbar_wait(&acc_full[as], accphase, p.status, 540 + as);
+      mbar_wait(&acc_full[as], accphase, p.status, 570 + as);
       if (p.dbg) { const long long t = clock64(); c_wait_acc += t - tq; tq = t; }
       tc_fence_after();
 #pragma unroll 1
-      for (int g = eh; g < kBandRows / kPool; g += 2) {
-        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * 256 + g * (kPool * kBandWins);
+      for (int g = 0; g < kBandRows / kPool; ++g) {
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * kWgN + g * (kPool * kBandWins);
         float m[kBandWins];
-        uint32_t r[32];
+        uint32_t r[32], r2[32];
         tmem_ld_32x32(lane_addr, r);                           // positions 0..3 of the pool group x 8 windows
+        tmem_ld_32x32(lane_addr + 32, r2);                     // positions 4..7
         tmem_wait_ld();
 #pragma unroll
-        for (int w = 0; w < kBandWins; ++w)
-          m[w] = fmaxf(fmaxf(__uint_as_float(r[w]), __uint_as_float(r[8 + w])), fmaxf(__uint_as_float(r[16 + w]), __uint_as_float(r[24 + w])));
-        tmem_ld_32x32(lane_addr + 32, r);                      // positions 4..7
-        tmem_wait_ld();
-#pragma unroll
-        for (int w = 0; w < kBandWins; ++w)
-          m[w] = fmaxf(m[w], fmaxf(fmaxf(__uint_as_float(r[w]), __uint_as_float(r[8 + w])), fmaxf(__uint_as_float(r[16 + w]), __uint_as_float(r[24 + w]))));
+        for (int w = 0; w < kBandWins; ++w) {
+          const float ma = fmaxf(fmaxf(__uint_as_float(r[w]), __uint_as_float(r[8 + w])), fmaxf(__uint_as_float(r[16 + w]), __uint_as_float(r[24 + w])));
+          const float mb = fmaxf(fmaxf(__uint_as_float(r2[w]), __uint_as_float(r2[8 + w])), fmaxf(__uint_as_float(r2[16 + w]), __uint_as_float(r2[24 + w])));
+          m[w] = fmaxf(ma, mb);
+        }
         const int gg = band * (kBandRows / kPool) + g;
         if (gg < kPooled && !(p.experiment & 128)) {
 #pragma unroll
@@ -406,7 +403,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const __grid_const
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (p.dbg) c_epi += clock64() - tq;
     }
-    if (p.dbg && ew == 0 && lane == 0) {
+    if (p.dbg && wq == 0 && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 8;
       d[3] = c_wait_acc; d[4] = c_epi;
     }

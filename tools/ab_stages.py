@@ -43,7 +43,6 @@ def main():
             clf.set_option("fuse_gather", 1)
             clf.set_option("conv_cluster", 1)
             clf.set_option("tail_overlap", 1)
-            clf.set_option("wv_tmem_a", 0)
             for kv in cfg.split(","):
                 k, v = kv.split("=")
                 clf.set_option(k, int(v))
@@ -94,7 +93,7 @@ def wvg_cycles(clf, pool, bits=0):
     d = clf.debug_fetch("conv_dbg", 1).cpu().view(torch.int64).numpy().astype(float)
     clf.set_option("conv_experiment", 0)
     units = max(d[:, 5].mean(), 1)
-    print(f"wv_gather_kernel (IGLOO#1) cycle breakdown, experiment bits {bits}, mean over CTAs (warp 4 = a gather warp, warp 16 = an epilogue warp, warp 1 = MMA issuer):")
+    print(f"wv_gather_kernel (IGLOO#1) cycle breakdown, experiment bits {bits}, mean over CTAs (warp 4 = a gather warp, warp 20 = an epilogue warp, warp 1 = MMA issuer):")
     for i, nm in enumerate(names):
         print(f"   {nm:42s} {d[:, i].mean():12.0f}   per unit {d[:, i].mean() / units:9.0f}   (min {d[:, i].min():.0f}, max {d[:, i].max():.0f})")
 
