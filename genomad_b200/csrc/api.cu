@@ -150,11 +150,10 @@ static int get_encode_fn(PFN_encodeTiled* fn) {
 
 // activations [n][5997][768 B] viewed as bytes; box = 128 bytes (one plane slice) x 136 rows x 1 window, 128B swizzle,
 // rows outside [0, 5997) read as 0 (= causal padding)
-static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows, int box_rows = kSlabRows,
-                        int box_windows = 1) {
+static int make_act_map(PFN_encodeTiled enc, CUtensorMap* tm, uint8_t* base, int n_windows, int box_rows = kSlabRows) {
   cuuint64_t dims[3] = {kRowBytes, kTok, static_cast<cuuint64_t>(n_windows)};
   cuuint64_t strides[2] = {kRowBytes, static_cast<cuuint64_t>(kTok) * kRowBytes};
-  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_windows)};
+  cuuint32_t box[3] = {128, static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -193,7 +193,15 @@ uint32_t gnm_crc32c(const void* data, size_t n);
  * become wrong), 4 / 8 = collect per-CTA cycle counters of conv3 / conv2 (gnm_debug_fetch "conv_dbg");
  * "fuse_l1" 1 = run layer 1 and the first IGLOO kernel's value projection as ONE kernel (csrc/layer1_wv.cuh: SIMT producers
  * write the tensor core's B operand straight into swizzled shared memory; bit-identical results, 17 instead of 18 launches
- * per step; measured slower than the two separate kernels at the end of round 1, hence 0 by default). */
+ * per step; measured slower than the two separate kernels at the end of round 1, hence 0 by default);
+ * "fuse_gather" 1 (default) = IGLOO value projection + patch gather in one pass over the activations (csrc/wv_gather.cuh),
+ * 0 = the round-1 pair conv_t_kernel<true> + patch_stream_kernel (A/B baseline and cross-check);
+ * "tail_overlap" 1 (default) = calls that span several internal steps run each step's tail (logits, attention, head) on a
+ * second stream next to the next step's main part; 0 = strictly in order (bitwise identical results);
+ * "conv_cluster" 1 (default), 2, 4, 8 = thread-block cluster size of the conv kernel's launch (experiment, measured slower);
+ * "wv_cost_group" per-mille weight of a band's position groups in the fused IGLOO kernel's unit split (default 100; experiment);
+ * further "conv_experiment" bits for wv_gather_kernel: 32 = no gather, 64 = no part_t stores, 128 = no q stores, 256 = gather
+ * reads only, 512 = cycle counters (gnm_debug_fetch "conv_dbg"), 1024 = no weight loads, 2048 = no ldmatrix. */
 int gnm_set_option(gnm_handle* h, const char* name, int value);
 int gnm_get_option(gnm_handle* h, const char* name, int* value);
 
