@@ -189,7 +189,7 @@ wv_gather_kernel(const __grid_constant__ CUtensorMap tm_band, const WvGatherPara
         mbar_arrive_expect_tx(&a_full[b], kWgRegion);
         // k: 0 hi16 channels 0-63, 1 lo16 channels 0-63, 2 hi16 channels 64-127, 3 lo16 channels 64-127 (byte offset in the row)
         const int src = (k & 1 ? kOffLo16 : kOffHi16) + (k >> 1) * 128;
-        tma_load_3d_hint(s_a + b * kWgRegion, &tm_band, &a_full[b], src, w0, band * kBandRows, pol);     // box = {128 B, 8 windows, 32 positions}
+        tma_load_3d_hint(s_a + b * kWgRegion, &tm_band, &a_full[b], src, w0, band * kBandRows, pol);     // box = {128 B, 8 windows, 24 positions}
       }
       b0 += 4; if (b0 >= kWgBufs) b0 -= kWgBufs;
     }

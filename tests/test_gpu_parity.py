@@ -515,8 +515,9 @@ def test_activation_range_overflow_is_reported(shipped):
 
 def test_fused_wv_gather_vs_separate_kernels(shipped):
     """Round 2: the IGLOO value projection and the patch gather share one pass over the activations (csrc/wv_gather.cuh,
-    band-major units of 32 positions x 8 windows).  Against the round-1 pair (conv_t_kernel<true> + patch_stream_kernel,
-    option fuse_gather=0): q is bitwise identical (same MMA sequence per output), mpi agrees to fp32 re-association level,
+    band-major units of 24 positions x 8 windows; gather on warp-level mma with fp16 hi / lo operand halves).  Against the round-1
+    pair (conv_t_kernel<true> + patch_stream_kernel, option fuse_gather=0): q is bitwise identical (same MMA sequence per output),
+    mpi agrees to fp32 re-association level,
     probabilities to 1e-6 -- with live (synthetic) IGLOO weights, batches that are not multiples of 8 and a batch of 1."""
     from genomad_b200.engine import Classifier
     w = M.synthetic_igloo_weights(shipped)
