@@ -226,6 +226,105 @@ static void pack_stage_f8_pairs(std::vector<uint8_t>& dst, const float* Wkn, int
     }
 }
 
+// One IGLOO layer's patch set as the gather kernels want it (host only).
+//   * fold the patch weights (Wf = w_mult * w_summer / 32, reference igloo.py:199-204 applied to rows that carry the activation
+//     scale), sort the 8,400 (patch, slot) entries by position and deal them to the kGsSlots entry slots (padding slots:
+//     position 0, zero weights): ent_w / ent_pos / slot_of -- patch_stream_kernel's and patch_finish*'s view;
+//   * wv_gather_kernel's view of the same sorted entries: POSITION GROUPS = the entries that sit on one position, at most
+//     kWgGroupMax = 4 per group (the 8 columns of the warp-level mma are 4 entries x (hi, lo); 8,400 entries hit ~4,500 positions),
+//     the first group of every band of kBandRows positions, and the folded weights as that instruction's B fragments: fp16 hi / lo
+//     halves of w * 2^k (k moves the largest weight to [2^13, 2^14) so that the lo halves stay in fp16's normal range; the kernel
+//     multiplies the sums by unscale = 2^-k).  Fragment word order per slot: [K-half][k-step][tig] x {hi b0, hi b1, lo b0, lo b1},
+//     b0 = channels (k0, k0 + 1), b1 = (k0 + 8, k0 + 9), k0 = 64 K-half + 16 k-step + 2 tig.
+struct PatchPack {
+  std::vector<float> ent_w;              // [kGsSlots][128]
+  std::vector<int32_t> ent_pos, slot_of; // [kGsSlots], [8400]
+  std::vector<int2> groups;              // {first slot, row inside the band | entries << 8}
+  std::vector<int32_t> band_gstart;      // [kNumBands + 1]
+  std::vector<uint32_t> frag;            // [kGsSlots][128]
+  float unscale = 1.f;
+};
+static void pack_patches(const int32_t* patches, const float* w_mult, const float* w_summer, PatchPack& o) {
+  std::vector<int> order(static_cast<size_t>(kPatches) * kPatchLen);
+  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return patches[a] < patches[b]; });
+  o.ent_w.assign(static_cast<size_t>(kGsSlots) * kC, 0.f);
+  o.ent_pos.assign(kGsSlots, 0);
+  o.slot_of.assign(static_cast<size_t>(kPatches) * kPatchLen, 0);
+  std::vector<float>& ent_w = o.ent_w;
+  std::vector<int32_t>& ent_pos = o.ent_pos;
+  for (size_t slot = 0; slot < order.size(); ++slot) {
+    const int e = order[slot], k = e % kPatchLen;
+    ent_pos[slot] = patches[e];
+    o.slot_of[e] = static_cast<int32_t>(slot);
+    for (int c = 0; c < kC; ++c)
+      ent_w[slot * kC + c] = (w_mult[static_cast<size_t>(e) * kC + c] * w_summer[k * kC + c]) * (1.f / kActScale);
+  }
+  float wmax = 0.f;
+  for (float v : ent_w) wmax = std::max(wmax, std::fabs(v));
+  int k2 = 0;
+  if (wmax > 0.f && std::isfinite(wmax)) { int ex; std::frexp(wmax, &ex); k2 = std::max(-24, std::min(40, 14 - ex)); }   // wmax * 2^k2 in [2^13, 2^14)
+  const float wscale = std::ldexp(1.f, k2);
+  o.unscale = std::ldexp(1.f, -k2);
+  o.groups.clear();
+  o.band_gstart.assign(kNumBands + 1, 0);
+  const size_t n_ent = order.size();
+  size_t slot = 0;
+  for (int b = 0; b < kNumBands; ++b) {
+    o.band_gstart[b] = static_cast<int32_t>(o.groups.size());
+    while (slot < n_ent && ent_pos[slot] < (b + 1) * kBandRows) {
+      size_t run = slot;
+      while (run < n_ent && ent_pos[run] == ent_pos[slot] && run - slot < static_cast<size_t>(kWgGroupMax)) ++run;
+      o.groups.push_back(make_int2(static_cast<int>(slot), (ent_pos[slot] - b * kBandRows) | (static_cast<int>(run - slot) << 8)));
+      slot = run;
+    }
+  }
+  o.band_gstart[kNumBands] = static_cast<int32_t>(o.groups.size());
+  if (o.groups.empty()) o.groups.push_back(make_int2(0, 0));
+  auto h2 = [](float x, float y) {
+    return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(x))) | (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(y))) << 16);
+  };
+  o.frag.assign(static_cast<size_t>(kGsSlots) * 128, 0u);      // 512 B per entry slot
+  for (size_t e = 0; e < n_ent; ++e)
+    for (int kh = 0; kh < 2; ++kh)
+      for (int ks = 0; ks < 4; ++ks)
+        for (int tig = 0; tig < 4; ++tig) {
+          const int k0 = kh * 64 + ks * 16 + 2 * tig;
+          const int kk[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
+          float hi[4], lo[4];
+          for (int i = 0; i < 4; ++i) {
+            const float x = ent_w[e * kC + kk[i]] * wscale;
+            hi[i] = __half2float(__float2half_rn(x));
+            lo[i] = x - hi[i];
+          }
+          uint32_t* f = &o.frag[(((e * 2 + kh) * 4 + ks) * 4 + tig) * 4];
+          f[0] = h2(hi[0], hi[1]); f[1] = h2(hi[2], hi[3]); f[2] = h2(lo[0], lo[1]); f[3] = h2(lo[2], lo[3]);
+        }
+}
+// Test hook (host only): the packing above for one IGLOO layer, into caller-owned buffers; see include/gnm.h.
+extern "C" int gnm_pack_patches(const int32_t* patches, const float* w_mult, const float* w_summer, int32_t* slot_of, int32_t* ent_pos,
+                                float* ent_w, int32_t* groups, int* n_groups, int32_t* band_first_group, uint32_t* frag, float* unscale,
+                                int* layout) {
+  if (layout) { layout[0] = kBandRows; layout[1] = kNumBands; layout[2] = kGsSlots; layout[3] = kWgGroupMax; }
+  if (!patches && !w_mult && !w_summer) return 0;                       // layout query only
+  if (!patches || !w_mult || !w_summer || !n_groups) return fail("gnm_pack_patches: null argument");
+  for (int i = 0; i < kPatches * kPatchLen; ++i)
+    if (patches[i] < 0 || patches[i] >= kTok) return fail("gnm_pack_patches: patch index out of range");
+  PatchPack pk;
+  pack_patches(patches, w_mult, w_summer, pk);
+  const int real_groups = pk.band_gstart[kNumBands];
+  if (groups && *n_groups < real_groups) return fail("gnm_pack_patches: groups buffer too small");
+  if (slot_of) std::memcpy(slot_of, pk.slot_of.data(), pk.slot_of.size() * sizeof(int32_t));
+  if (ent_pos) std::memcpy(ent_pos, pk.ent_pos.data(), pk.ent_pos.size() * sizeof(int32_t));
+  if (ent_w) std::memcpy(ent_w, pk.ent_w.data(), pk.ent_w.size() * sizeof(float));
+  if (groups) for (int i = 0; i < real_groups; ++i) { groups[2 * i] = pk.groups[i].x; groups[2 * i + 1] = pk.groups[i].y; }
+  *n_groups = real_groups;
+  if (band_first_group) std::memcpy(band_first_group, pk.band_gstart.data(), pk.band_gstart.size() * sizeof(int32_t));
+  if (frag) std::memcpy(frag, pk.frag.data(), pk.frag.size() * sizeof(uint32_t));
+  if (unscale) *unscale = pk.unscale;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_handle** out) {
   if (!w || !out) return fail("gnm_create: null argument");
@@ -322,71 +421,16 @@ extern "C" int gnm_create(int device, const gnm_weights* w, int max_batch, gnm_h
   // ---- IGLOO weights
   for (int s = 0; s < 2; ++s) {
     const gnm_igloo_weights& g = w->igloo[s];
-    // fold the patch weights, then sort the 8400 (patch, slot) entries by position and deal them to the
-    // kGsSlots entry slots of patch_stream_kernel (padding slots: position 0, zero weights)
-    std::vector<int> order(static_cast<size_t>(kPatches) * kPatchLen);
-    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g.patches[a] < g.patches[b]; });
-    std::vector<float> ent_w(static_cast<size_t>(kGsSlots) * kC, 0.f);
-    std::vector<int32_t> ent_pos(kGsSlots, 0), slot_of(static_cast<size_t>(kPatches) * kPatchLen, 0);
-    for (size_t slot = 0; slot < order.size(); ++slot) {
-      const int e = order[slot], k = e % kPatchLen;
-      ent_pos[slot] = g.patches[e];
-      slot_of[e] = static_cast<int32_t>(slot);
-      for (int c = 0; c < kC; ++c)
-        ent_w[slot * kC + c] = (g.w_mult[static_cast<size_t>(e) * kC + c] * g.w_summer[k * kC + c]) * (1.f / kActScale);
-    }
-    {
-      // wv_gather_kernel's view of the same sorted entries: POSITION GROUPS = the entries that sit on one position, at most
-      // kWgGroupMax = 8 per group (the N of the warp-level mma the gather runs on; 8,400 entries hit ~4,500 positions), and the
-      // folded weights as that instruction's B fragments: fp16 hi / lo halves of w * 2^k (k moves the largest weight to ~2^14 so
-      // that the lo halves stay in fp16's normal range; the kernel multiplies the sums by 2^-k).
-      float wmax = 0.f;
-      for (float v : ent_w) wmax = std::max(wmax, std::fabs(v));
-      int k2 = 0;
-      if (wmax > 0.f && std::isfinite(wmax)) { int ex; std::frexp(wmax, &ex); k2 = std::max(-24, std::min(40, 14 - ex)); }   // wmax * 2^k2 in [2^13, 2^14)
-      const float wscale = std::ldexp(1.f, k2);
-      h->gather_unscale[s] = std::ldexp(1.f, -k2);
-      std::vector<int2> groups;
-      std::vector<int32_t> gs(kNumBands + 1, 0);
-      const size_t n_ent = order.size();
-      size_t slot = 0;
-      for (int b = 0; b < kNumBands; ++b) {
-        gs[b] = static_cast<int32_t>(groups.size());
-        while (slot < n_ent && ent_pos[slot] < (b + 1) * kBandRows) {
-          size_t run = slot;
-          while (run < n_ent && ent_pos[run] == ent_pos[slot] && run - slot < static_cast<size_t>(kWgGroupMax)) ++run;
-          groups.push_back(make_int2(static_cast<int>(slot), (ent_pos[slot] - b * kBandRows) | (static_cast<int>(run - slot) << 8)));
-          slot = run;
-        }
-      }
-      gs[kNumBands] = static_cast<int32_t>(groups.size());
-      if (groups.empty()) groups.push_back(make_int2(0, 0));
-      h->band_groups[s].resize(kNumBands);
-      for (int b = 0; b < kNumBands; ++b) h->band_groups[s][b] = gs[b + 1] - gs[b];
-      auto h2 = [](float x, float y) {
-        return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(x))) | (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(y))) << 16);
-      };
-      std::vector<uint32_t> frag(static_cast<size_t>(kGsSlots) * 128, 0u);      // 512 B per entry slot
-      for (size_t e = 0; e < n_ent; ++e)
-        for (int kh = 0; kh < 2; ++kh)
-          for (int ks = 0; ks < 4; ++ks)
-            for (int tig = 0; tig < 4; ++tig) {
-              const int k0 = kh * 64 + ks * 16 + 2 * tig;
-              const int kk[4] = {k0, k0 + 1, k0 + 8, k0 + 9};
-              float hi[4], lo[4];
-              for (int i = 0; i < 4; ++i) {
-                const float x = ent_w[e * kC + kk[i]] * wscale;
-                hi[i] = __half2float(__float2half_rn(x));
-                lo[i] = x - hi[i];
-              }
-              uint32_t* f = &frag[(((e * 2 + kh) * 4 + ks) * 4 + tig) * 4];
-              f[0] = h2(hi[0], hi[1]); f[1] = h2(hi[2], hi[3]); f[2] = h2(lo[0], lo[1]); f[3] = h2(lo[2], lo[3]);
-            }
-      if (dev_upload(h, &h->grp[s], groups.data(), groups.size())) return 1;
-      if (dev_upload(h, &h->band_gstart[s], gs.data(), gs.size())) return 1;
-      if (dev_upload(h, reinterpret_cast<uint32_t**>(&h->wfrag[s]), frag.data(), frag.size())) return 1;
-    }
+    PatchPack pk;
+    pack_patches(g.patches, g.w_mult, g.w_summer, pk);
+    h->gather_unscale[s] = pk.unscale;
+    h->band_groups[s].resize(kNumBands);
+    for (int b = 0; b < kNumBands; ++b) h->band_groups[s][b] = pk.band_gstart[b + 1] - pk.band_gstart[b];
+    if (dev_upload(h, &h->grp[s], pk.groups.data(), pk.groups.size())) return 1;
+    if (dev_upload(h, &h->band_gstart[s], pk.band_gstart.data(), pk.band_gstart.size())) return 1;
+    if (dev_upload(h, reinterpret_cast<uint32_t**>(&h->wfrag[s]), pk.frag.data(), pk.frag.size())) return 1;
+    const std::vector<float>& ent_w = pk.ent_w;
+    const std::vector<int32_t>&ent_pos = pk.ent_pos, &slot_of = pk.slot_of;
     if (dev_upload(h, &h->ent_w[s], ent_w.data(), ent_w.size())) return 1;
     if (dev_upload(h, &h->ent_pos[s], ent_pos.data(), ent_pos.size())) return 1;
     if (dev_upload(h, &h->slot_of[s], slot_of.data(), slot_of.size())) return 1;

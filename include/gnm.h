@@ -205,6 +205,26 @@ uint32_t gnm_crc32c(const void* data, size_t n);
 int gnm_set_option(gnm_handle* h, const char* name, int value);
 int gnm_get_option(gnm_handle* h, const char* name, int* value);
 
+/*
+ * Host-only test hook (no GPU needed): how gnm_create lays out one IGLOO layer's patch set for the gather kernels
+ * (csrc/api.cu pack_patches; reference semantics igloo.py:192-206: gather_nd(patches) * w_mult, reshaped, @ w_summer).
+ *   layout[4]   (out, optional): {positions per band, bands, entry slots, max entries per position group}
+ *   patches [2100][4], w_mult [2100][4][128], w_summer [512] as in gnm_igloo_weights; with all three NULL only `layout` is filled
+ *   slot_of [8400]            entry slot of (patch, k); slots are sorted by position
+ *   ent_pos [slots]           position of every slot;  ent_w [slots][128] folded weights w_mult * w_summer / 32
+ *   groups [*n_groups][2]     {first slot, row inside the band | entries << 8}: the entries (<= 4) on one position; *n_groups is
+ *                             the capacity on input and the number of groups on output
+ *   band_first_group [bands + 1]
+ *   frag [slots][128] words   the folded weights * 2^k as mma.m16n8k16 B fragments: per slot [K-half 2][k-step 4][tig 4] x
+ *                             {hi b0, hi b1, lo b0, lo b1}, each word two fp16: b0 = channels (k0, k0 + 1), b1 = (k0 + 8, k0 + 9),
+ *                             k0 = 64 K-half + 16 k-step + 2 tig; hi = fp16(w 2^k), lo = fp16(w 2^k - hi)
+ *   unscale                   2^-k
+ * Any output pointer may be NULL.
+ */
+int gnm_pack_patches(const int32_t* patches, const float* w_mult, const float* w_summer, int32_t* slot_of, int32_t* ent_pos,
+                     float* ent_w, int32_t* groups, int* n_groups, int32_t* band_first_group, uint32_t* frag, float* unscale,
+                     int* layout);
+
 /* Number of kernels this library has launched through handle h (monotonic). */
 long long gnm_kernel_launches(gnm_handle* h);
 

@@ -119,6 +119,125 @@ def test_library_exports_every_declared_symbol(repo_root):
     assert b"sm_100a" in lib.gnm_version()
 
 
+def _pack_patches(patches, w_mult, w_summer):
+    """gnm_pack_patches through ctypes -> dict of numpy arrays (host only)."""
+    lib = engine.load_library()
+    lay = (ctypes.c_int * 4)()
+    assert lib.gnm_pack_patches(None, None, None, None, None, None, None, None, None, None, None, lay) == 0
+    band_rows, n_bands, slots, group_max = list(lay)
+    out = {"band_rows": band_rows, "n_bands": n_bands, "slots": slots, "group_max": group_max,
+           "slot_of": np.empty(8400, np.int32), "ent_pos": np.empty(slots, np.int32), "ent_w": np.empty((slots, 128), np.float32),
+           "groups": np.empty((8400, 2), np.int32), "band_first": np.empty(n_bands + 1, np.int32),
+           "frag": np.empty((slots, 2, 4, 4, 4), np.uint32)}
+    n_groups = ctypes.c_int(8400)
+    unscale = ctypes.c_float(0)
+    p = np.ascontiguousarray(patches, np.int32)
+    wm = np.ascontiguousarray(w_mult, np.float32)
+    ws = np.ascontiguousarray(w_summer, np.float32)
+    rc = lib.gnm_pack_patches(p.ctypes.data, wm.ctypes.data, ws.ctypes.data, out["slot_of"].ctypes.data, out["ent_pos"].ctypes.data,
+                              out["ent_w"].ctypes.data, out["groups"].ctypes.data, ctypes.byref(n_groups), out["band_first"].ctypes.data,
+                              out["frag"].ctypes.data, ctypes.byref(unscale), None)
+    assert rc == 0, lib.gnm_last_error()
+    out["groups"] = out["groups"][:n_groups.value]
+    out["unscale"] = unscale.value
+    return out
+
+
+def _frag_halves(words):
+    """uint32 words of two fp16 -> float32 [..., 2] (low half first)."""
+    w = np.ascontiguousarray(words, np.uint32)
+    return w.view(np.uint16).reshape(w.shape + (2,)).view(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["random", "one_position", "ends"])
+def test_patch_packing_for_the_fused_gather(kind):
+    """Host logic of the fused IGLOO kernel (csrc/api.cu pack_patches; kernel side csrc/wv_gather.cuh): every (patch, k) entry
+    lands in exactly one position group of <= 4 entries that share a position inside the right band, and the mma B fragments
+    reproduce the folded weights w_mult * w_summer / 32 (reference igloo.py:199-204) to fp32 accuracy.  Then the kernel's
+    arithmetic is replayed in NumPy on random activations: sum over the fragment lanes of (hi16 + lo16 row) x (hi + lo weight
+    half) with the kernel's channel mapping == the plain dot product."""
+    rng = np.random.default_rng(5)
+    if kind == "random":
+        patches = rng.integers(0, 5997, size=(2100, 4), dtype=np.int32)
+    elif kind == "one_position":
+        patches = np.full((2100, 4), 3001, np.int32)
+    else:
+        patches = np.tile(np.asarray([0, 1, 5995, 5996], np.int32), (2100, 1))
+    w_mult = (rng.standard_normal((2100, 4, 128)) * 0.05).astype(np.float32)
+    w_mult[7] = 0.0                                               # an all-zero patch
+    w_mult[8, 1, :5] = [1e-9, -3e-7, 2.5, -1e-4, 6e-6]              # a wide dynamic range inside one entry
+    w_summer = rng.standard_normal(512).astype(np.float32)
+    o = _pack_patches(patches, w_mult, w_summer)
+    R, NB, GM = o["band_rows"], o["n_bands"], o["group_max"]
+    assert NB * R >= 5997 > (NB - 1) * R and R % 8 == 0 and GM == 4
+
+    # slots: a permutation of the 8,400 entries, sorted by position, folded weights exact
+    flat_pos = patches.reshape(-1)
+    slot_of = o["slot_of"]
+    assert sorted(slot_of.tolist()) == list(range(8400))
+    assert np.array_equal(o["ent_pos"][slot_of], flat_pos)
+    assert np.all(np.diff(o["ent_pos"][:8400]) >= 0)
+    folded = (w_mult.reshape(8400, 128) * np.tile(w_summer.reshape(4, 128), (2100, 1))) * np.float32(1 / 32)
+    assert np.array_equal(o["ent_w"][slot_of], folded.astype(np.float32))
+
+    # groups: cover every slot once, in order; one position per group; row / band consistent; band table monotone
+    g = o["groups"]
+    first, row, ne = g[:, 0], g[:, 1] & 31, g[:, 1] >> 8
+    assert first[0] == 0 and np.array_equal(first[1:], first[:-1] + ne[:-1]) and first[-1] + ne[-1] == 8400
+    assert ne.min() >= 1 and ne.max() <= GM
+    bf = o["band_first"]
+    assert bf[0] == 0 and bf[-1] == len(g) and np.all(np.diff(bf) >= 0)
+    band_of_group = np.searchsorted(bf, np.arange(len(g)), side="right") - 1
+    for i in range(len(g)):
+        pos = o["ent_pos"][first[i]:first[i] + ne[i]]
+        assert np.all(pos == pos[0]) and pos[0] == band_of_group[i] * R + row[i] and row[i] < R
+    # a run of one position longer than 4 is split into consecutive groups, never merged across positions
+    same = o["ent_pos"][first[1:]] == o["ent_pos"][first[:-1]]
+    assert np.all(ne[:-1][same] == GM)
+
+    # fragments -> weights: w[e][k] = (hi + lo) * unscale, channel mapping k0 = 64 kh + 16 ks + 2 tig, (k0, k0+1 | k0+8, k0+9)
+    halves = _frag_halves(o["frag"][:8400])                      # [e][kh][ks][tig][word 4][half 2]
+    w_rec = np.zeros((8400, 128), np.float64)
+    for kh in range(2):
+        for ks in range(4):
+            for tig in range(4):
+                k0 = 64 * kh + 16 * ks + 2 * tig
+                hi_b0, hi_b1, lo_b0, lo_b1 = (halves[:, kh, ks, tig, j].astype(np.float64) for j in range(4))
+                w_rec[:, [k0, k0 + 1]] = hi_b0 + lo_b0
+                w_rec[:, [k0 + 8, k0 + 9]] = hi_b1 + lo_b1
+    w_rec *= o["unscale"]
+    ref = o["ent_w"][:8400].astype(np.float64)
+    scale = np.abs(ref).max()
+    assert np.abs(w_rec - ref).max() <= 2.0 ** -21 * scale        # hi + lo carry >= 21 bits of the largest weight
+    big = np.abs(ref) >= scale * 2.0 ** -10
+    assert np.abs(w_rec[big] / ref[big] - 1).max() <= 2.0 ** -20
+    assert np.all(o["frag"][8400:] == 0)                          # padding slots
+
+    # replay of wv_gather_kernel's gather on 8 windows of random activations (hi16 / lo16 planes of 32 * y)
+    y = (rng.standard_normal((8, 5997, 128)) * 3).astype(np.float32) * np.float32(32)
+    y_hi = y.astype(np.float16)
+    y_lo = (y - y_hi.astype(np.float32)).astype(np.float16)
+    for gi in rng.choice(len(g), size=min(64, len(g)), replace=False):
+        e0, n_e = int(first[gi]), int(ne[gi])
+        pos = int(o["ent_pos"][e0])
+        a_hi, a_lo = y_hi[:, pos, :].astype(np.float64), y_lo[:, pos, :].astype(np.float64)
+        got = np.zeros((8, n_e))
+        for kh in range(2):
+            for ks in range(4):
+                for tig in range(4):
+                    k0 = 64 * kh + 16 * ks + 2 * tig
+                    ks4 = [k0, k0 + 1, k0 + 8, k0 + 9]
+                    for t in range(n_e):
+                        hh = halves[e0 + t, kh, ks, tig].astype(np.float64)          # [word][half]
+                        b_hi = np.array([hh[0, 0], hh[0, 1], hh[1, 0], hh[1, 1]])    # column 2t   (hi weight half)
+                        b_lo = np.array([hh[2, 0], hh[2, 1], hh[3, 0], hh[3, 1]])    # column 2t+1 (lo weight half)
+                        got[:, t] += (a_hi[:, ks4] + a_lo[:, ks4]) @ (b_hi + b_lo)
+        got *= o["unscale"]
+        want = (y[:, pos, :].astype(np.float64)) @ ref[e0:e0 + n_e].T
+        tol = 1e-6 * max(np.abs(want).max(), 1.0)
+        assert np.abs(got - want).max() <= tol, (kind, gi, np.abs(got - want).max(), tol)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
