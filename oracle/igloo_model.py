@@ -1,9 +1,15 @@
 """
 CPU restatement (PyTorch, fp32 or fp64) of the geNomad IGLOO1D classifier.
-TEST INFRASTRUCTURE (see oracle/__init__.py).  **PARITY UNPINNED** against
-TensorFlow/Keras: TF/Keras/h5py cannot be installed in the build container and the
-reference has no model tests or golden vectors.  What is here follows the reference
-source text:
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Pinning status.  STRUCTURE PINNED, TensorFlow's arithmetic unpinned: TF / Keras / h5py cannot be installed in the build
+container and the reference has no model tests, but the reference's own model definition (genomad/neural_network/model.py and
+igloo.py, imported by path) runs on a NumPy stand-in for the ~25 TF / Keras calls it makes (tests/golden/keras_shim.py).  Its
+outputs for 24 windows -- create_classifier() -> load_weights(nn_classifier.h5) -> predict, shipped weights and synthetic O(1)
+IGLOO weights -- are committed (tests/golden/reference_graph_golden.npz, generator make_reference_graph_golden.py) and this
+restatement agrees with them to 5e-14 in fp64 (tests/test_oracle_golden.py::test_oracle_model_matches_reference_graph).  The
+semantics of the library calls themselves (causal Conv1D, gather_nd, MaxPool1D, BatchNormalization(eps=1e-3) ...) are the
+documented ones, restated in that stand-in.  What is here follows the reference source text:
 
   one-hot                 genomad/neural_network/model.py:9-11
   encoder graph           genomad/neural_network/model.py:14-31

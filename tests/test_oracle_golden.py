@@ -96,6 +96,109 @@ def test_synthetic_weights_make_attention_live(golden_dir, weights_npz):
     assert float(parts["ig0"]["alpha"].max()) > 5.0 / 749    # synthetic weights: far from uniform
 
 
+def test_oracle_model_matches_reference_graph(golden_dir, weights_npz):
+    """The model oracle against vectors produced by the REFERENCE'S OWN model definition: genomad/neural_network/{model,igloo}.py
+    imported by path and executed -- create_classifier(), load_weights(nn_classifier.h5), predict -- on a NumPy stand-in for the
+    TensorFlow / Keras calls they make (tests/golden/keras_shim.py, generator make_reference_graph_golden.py; neither library
+    exists in this image).  In fp64 the oracle and the reference graph must agree to rounding (structure: layer sequence, the
+    gather_nd / transpose / reshape chain, pooling, softmax axes, dataset -> layer mapping), with the shipped weights AND with
+    synthetic O(1) IGLOO weights (live gather / logits / softmax); in fp32 to summation-order noise.  TensorFlow's own fp32
+    arithmetic is not pinned by this."""
+    g = np.load(golden_dir / "reference_graph_golden.npz")
+    tok = g["tokens"]
+    assert tok.shape == (24, 5997) and np.array_equal(tok, T.tokenize_windows(g["windows"]))
+    w = M.load_npz_weights(weights_npz)
+    wsyn = M.synthetic_igloo_weights(w)
+    # the loader of the reference graph consumed all 32 datasets of the file, each into the variable of the same name
+    rep = [str(r) for r in g["load_report"]]
+    assert len(rep) == 32 and len({r.split(" -> ")[1].split(" ")[0] for r in rep}) == 32
+    assert "/model/igloo1d_kernel/random_patches:0 -> igloo1d_kernel/random_patches (2100, 4, 1) int32" in rep
+    assert "/dense_2/dense_2/kernel:0 -> dense_2/kernel (512, 3) float32" in rep
+    # the encoder the reference builds: conv -> IGLOO#0 on conv1's output, two more convs -> IGLOO#1, concatenate, dense, BN, relu
+    names = [str(n) for n in g["layer_names"]]
+    enc = names[:names.index("|")]
+    assert [n for n in enc if n.startswith(("conv1d", "igloo1d", "concat", "dense", "batch"))] == \
+        ["conv1d", "igloo1d_kernel", "conv1d_1", "conv1d_2", "igloo1d_kernel_1", "concatenate", "dense", "batch_normalization"]
+    for key, ww in (("shipped", w), ("synthetic", wsyn)):
+        o64 = np.concatenate([M.forward(tok[i:i + 8], ww, torch.float64) for i in range(0, 24, 8)])
+        o32 = np.concatenate([M.forward(tok[i:i + 8], ww, torch.float32) for i in range(0, 24, 8)])
+        d64 = np.abs(o64 - g[key + "_fp64"]).max()
+        d32 = np.abs(o32 - g[key]).max()
+        assert d64 <= 1e-11, (key, d64)
+        assert d32 <= 5e-5 and np.abs(o32 - g[key + "_fp64"]).max() <= 5e-5, (key, d32)
+        assert np.array_equal(o32.argmax(1), g[key + "_fp64"].argmax(1))
+    # live weights really exercise the attention: the synthetic probabilities differ from the shipped ones
+    assert np.abs(g["synthetic_fp64"] - g["shipped_fp64"]).max() > 1e-3
+
+
+def test_reference_graph_golden_is_reproducible(golden_dir):
+    """Where the reference checkout exists (the build container; not the GPU box): rebuild the reference graph from its source and
+    re-predict three windows -- the committed fixture must be what the committed generator produces."""
+    import sys
+    from pathlib import Path
+    if not Path("/root/reference/genomad/neural_network/model.py").exists():
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "keras", "keras.layers", "keras.regularizers", "genomad",
+                                             "genomad.neural_network", "genomad.neural_network.igloo", "genomad.neural_network.model")}
+    try:
+        import make_reference_graph_golden as G
+        np.random.seed(0)
+        model_mod, igloo_mod = G.load_reference_model_module()
+        clf = model_mod.create_classifier()
+        clf.load_weights("/root/reference/genomad/data/nn_classifier.h5")
+        g = np.load(golden_dir / "reference_graph_golden.npz")
+        pick = [0, 13, 20]
+        p = clf.predict(g["tokens"][pick].astype(np.int64), batch_size=3)
+        assert np.abs(p - g["shipped"][pick]).max() <= 1e-6
+        assert [str(r) for r in g["load_report"]] == [f"{a} -> {b} {c} {d}" for a, b, c, d in clf.load_report]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_keras_stand_in_semantics():
+    """Spot checks of tests/golden/keras_shim.py against hand-computed values of the Keras / TF definitions it follows."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import keras_shim as K
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "keras", "keras.layers", "keras.regularizers")}
+    try:
+        tf, keras = K.install()
+        kl = keras.layers
+        # causal Conv1D: y[t] = b + sum_j x[t - (k-1) + j] W[j]
+        c = kl.Conv1D(1, 3, padding="causal")
+        x = np.arange(1, 6, dtype=np.float32).reshape(1, 5, 1)
+        c._run(x)
+        c.kernel.value = np.array([1, 10, 100], np.float32).reshape(3, 1, 1)
+        c.bias.value = np.array([0.5], np.float32)
+        assert np.allclose(c._run(x)[0, :, 0], [100.5, 210.5, 321.5, 432.5, 543.5])
+        # gather_nd with index depth 1, MaxPool1D valid, softmax, one_hot, BN inference, LeakyReLU
+        m = np.arange(24, dtype=np.float32).reshape(4, 3, 2)
+        assert np.array_equal(tf.gather_nd(m, np.array([[[3], [0]]])), m[[3, 0]][None])
+        assert np.array_equal(kl.MaxPool1D(pool_size=2)._run(np.array([[[1.], [5.], [2.], [3.], [9.]]]))[0, :, 0], [5., 3.])
+        assert np.allclose(tf.nn.softmax(np.array([[0., np.log(3.)]], np.float32)), [[0.25, 0.75]])
+        assert np.array_equal(tf.one_hot(np.array([[2, 0]]), depth=3), [[[0, 0, 1], [1, 0, 0]]])
+        bn = kl.BatchNormalization()
+        bn._run(np.zeros((1, 2), np.float32))
+        bn.gamma.value, bn.beta.value = np.array([2., 1.], np.float32), np.array([0.5, 0.], np.float32)
+        bn.moving_mean.value, bn.moving_variance.value = np.array([1., 0.], np.float32), np.array([0.003, 0.999], np.float32)
+        assert np.allclose(bn._run(np.array([[3., 2.]], np.float32)), [[2 * 2 / np.sqrt(0.004) + 0.5, 2.0]], rtol=1e-6)
+        assert np.allclose(kl.LeakyReLU(negative_slope=0.1)._run(np.array([[-2., 3.]], np.float32)), [[-0.2, 3.]])
+        # default layer names follow creation order per class
+        assert [kl.Dense(1).name, kl.Dense(1).name, kl.Conv1D(1, 1, padding="causal").name] == ["dense", "dense_1", "conv1d_1"]
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 def test_segment_mean():
     p = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], np.float32)
     out = T.segment_mean(p, np.array([0, 0, 2, 2]))
