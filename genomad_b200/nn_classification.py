@@ -302,6 +302,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             (enc_skip, cls_skip) in zip(jobs, plan):
         parsed = index = None
         names = preds = None
+        label = "Sequence" if what == "sequence" else "Provirus"      # the reference's log wording (nn_classification.py:333, 351, 407, 425)
         # ---- encode (here: record the window -> sequence map; the windows themselves are streamed to the GPU below)
         if enc_skip:
             console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
@@ -333,7 +334,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             console.log(f"{'Sequences' if what == 'sequence' else 'Proviruses'} classified.")
             if is_main:
                 np.savez_compressed(npz_path, **{names_key: names, "predictions": preds.astype(np.float32)})
-            console.log(f"{noun.capitalize()} classification in binary format written to {npz_path.name}.")
+            console.log(f"{label} classification in binary format written to {npz_path.name}.")
         if parsed is not None:
             parsed.close()
         if cleanup and is_main and enc_dir.is_dir():
@@ -341,7 +342,7 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
             shutil.rmtree(enc_dir)
         if is_main:
             _write_tsv(tsv_path, names, preds)
-        console.log(f"{noun.capitalize()} classification in tabular format written to {tsv_path.name}.")
+        console.log(f"{label} classification in tabular format written to {tsv_path.name}.")
 
     clf_pool.shutdown(wait=True)
     t_j = _time.perf_counter()

@@ -21,6 +21,7 @@ Semantics implemented (Keras 3 / TF 2 documentation):
   their default Keras names (a function of creation order in the reference's code) and variables by name, every variable exactly
   once with the saved shape (the reader is genomad_b200/h5lite.py).
 """
+import re
 import sys
 import types
 
@@ -325,10 +326,17 @@ class Model(Layer):
                 if isinstance(l, Model):
                     out.extend(all_layers(l))
             return out
-        by_name = {}
-        for l in all_layers(self):
-            assert l.name not in by_name, l.name
-            by_name[l.name] = l
+        # canonical names = the default names this model tree would have as the first model of a process (a second
+        # create_classifier() in the same process gets conv1d_3 ...; Keras' by-order loader does not care, so neither may this one)
+        by_name, per_base = {}, {}
+        order = {id(l): i for i, l in enumerate(_created)}
+        for l in sorted(all_layers(self), key=lambda l: order[id(l)]):
+            base = re.sub(r"_\d+$", "", l.name) if re.sub(r"_\d+$", "", l.name) in _counters else l.name
+            k = per_base.get(base, 0)
+            per_base[base] = k + 1
+            canon = base if k == 0 else f"{base}_{k}"
+            assert canon not in by_name, canon
+            by_name[canon] = l
         self.load_report = []
         hit = set()
         for ln in strs(f.attrs["/"]["layer_names"]):
@@ -380,7 +388,155 @@ def _tf_module():
     tf.reduce_mean = lambda a, axis=None: np.mean(np.asarray([_np(v) for v in a]) if isinstance(a, list) else _np(a), axis=axis)
     tf.nn = types.SimpleNamespace(softmax=lambda a: _softmax(_np(a)))
     tf.float32, tf.int64 = "float32", "int64"
+    _add_module_driver_calls(tf)
     return tf
+
+
+def _add_module_driver_calls(tf):
+    """The calls genomad/modules/nn_classification.py makes around the model: thread settings (no-ops), the TFRecord writer and
+    tf.train.Example (bytes via oracle/tfrecord.py, which tests/test_tfrecord_cpu.py checks against the real protobuf runtime),
+    FixedLenFeature / parse_single_example, a TFRecordDataset with map / batch / prefetch, gfile.glob, concat and segment_mean
+    (per-segment fp32 sum divided by the count, segment ids sorted as TF requires)."""
+    import glob as _glob
+    import struct
+    from oracle import tfrecord as R
+    tf.config = types.SimpleNamespace(threading=types.SimpleNamespace(set_inter_op_parallelism_threads=lambda n: None,
+                                                                        set_intra_op_parallelism_threads=lambda n: None))
+
+    class _Int64List:
+        def __init__(self, value=()):
+            self.value = [int(v) for v in value]
+
+    class _Feature:
+        def __init__(self, int64_list=None):
+            self.int64_list = int64_list
+
+    class _Features:
+        def __init__(self, feature=None):
+            self.feature = dict(feature or {})
+
+    class _Example:
+        def __init__(self, features=None):
+            self.features = features
+
+        def SerializeToString(self):
+            assert list(self.features.feature) == ["sequence"]
+            return R.serialize_example(self.features.feature["sequence"].int64_list.value)
+    tf.train = types.SimpleNamespace(Int64List=_Int64List, Feature=_Feature, Features=_Features, Example=_Example)
+
+    class _Writer:
+        def __init__(self, path):
+            self.f = open(path, "wb")
+
+        def write(self, record):
+            self.f.write(R.frame(record))
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            self.f.close()
+
+    class _FixedLenFeature:
+        def __init__(self, shape, dtype):
+            self.shape, self.dtype = list(shape), dtype
+
+    def _varint(buf, pos):
+        v = shift = 0
+        while True:
+            b = buf[pos]
+            pos += 1
+            v |= (b & 0x7F) << shift
+            shift += 7
+            if b < 128:
+                return v, pos
+
+    def _unwrap(buf, tag):
+        assert buf[0] == tag, (buf[0], tag)
+        n, pos = _varint(buf, 1)
+        assert pos + n <= len(buf)
+        return buf[pos:pos + n], buf[pos + n:]
+
+    def _parse_example(record):
+        features, rest = _unwrap(record, 0x0A)                  # Example.features
+        assert not rest
+        entry, rest = _unwrap(features, 0x0A)                   # Features.feature map entry
+        assert not rest
+        key, value = _unwrap(entry, 0x0A)
+        assert key == b"sequence"
+        feature, rest = _unwrap(value, 0x12)
+        assert not rest
+        int64_list, rest = _unwrap(feature, 0x1A)               # Feature.int64_list
+        assert not rest
+        packed, rest = _unwrap(int64_list, 0x0A)                # Int64List.value, packed varints
+        assert not rest
+        out, pos = [], 0
+        while pos < len(packed):
+            v, pos = _varint(packed, pos)
+            out.append(v)
+        return out
+
+    def parse_single_example(record, description):
+        (name, spec), = description.items()
+        tokens = np.asarray(_parse_example(record), np.int64)
+        assert name == "sequence" and list(tokens.shape) == spec.shape
+        return {name: tokens}
+
+    class _Dataset:
+        def __init__(self, it):
+            self._it = it
+
+        def __iter__(self):
+            return iter(self._it())
+
+        def map(self, fn, num_parallel_calls=None, deterministic=None):
+            src = self._it
+            return _Dataset(lambda: (fn(x) for x in src()))
+
+        def batch(self, n):
+            src = self._it
+
+            def gen():
+                buf = []
+                for x in src():
+                    buf.append(x)
+                    if len(buf) == n:
+                        yield np.stack(buf)
+                        buf = []
+                if buf:
+                    yield np.stack(buf)
+            return _Dataset(gen)
+
+        def prefetch(self, n):
+            return self
+
+    def _records(filenames):
+        for fn in filenames:
+            blob = open(fn, "rb").read()
+            pos = 0
+            while pos < len(blob):
+                (n,) = struct.unpack_from("<Q", blob, pos)
+                assert struct.unpack_from("<I", blob, pos + 8)[0] == R.masked_crc(blob[pos:pos + 8])
+                data = blob[pos + 12:pos + 12 + n]
+                assert struct.unpack_from("<I", blob, pos + 12 + n)[0] == R.masked_crc(data)
+                yield data
+                pos += 16 + n
+    tf.io = types.SimpleNamespace(TFRecordWriter=_Writer, FixedLenFeature=_FixedLenFeature, parse_single_example=parse_single_example,
+                                  gfile=types.SimpleNamespace(glob=lambda pat: _glob.glob(pat)))
+    tf.data = types.SimpleNamespace(TFRecordDataset=lambda filenames, num_parallel_reads=None: _Dataset(lambda: _records(list(filenames))),
+                                    experimental=types.SimpleNamespace(AUTOTUNE=-1))
+    tf.concat = lambda values, axis=0: np.concatenate([_np(v) for v in values], axis=axis)
+
+    def segment_mean(data, segment_ids):
+        data, ids = np.asarray(_np(data), np.float32), np.asarray(segment_ids).astype(np.int64)
+        assert len(ids) == len(data) and np.all(np.diff(ids) >= 0)
+        out = np.zeros((int(ids[-1]) + 1,) + data.shape[1:], np.float32)
+        cnt = np.zeros(len(out), np.float32)
+        for row, i in zip(data, ids):                           # sequential fp32 accumulation
+            out[i] += row
+            cnt[i] += 1
+        return out / np.maximum(cnt, 1)[:, None]
+    tf.math = types.SimpleNamespace(segment_mean=segment_mean)
 
 
 def install():
