@@ -298,17 +298,24 @@ def main(input_path, output_path, single_window, batch_size, restart, threads, v
     if not all(cls_skip for _, cls_skip in plan):
         clf_future = clf_pool.submit(_make_classifier, batch_size, info.local_rank)      # start now, overlap with indexing
 
+    # ---- stage 1, every job: "encode" (here: record the window -> sequence map; the windows themselves are streamed to the GPU in
+    # stage 2).  Like the reference, sequences AND proviruses are encoded before either is classified (nn_classification.py:215-281).
+    staged = []
     for (what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows), \
             (enc_skip, cls_skip) in zip(jobs, plan):
         parsed = index = None
-        names = preds = None
-        label = "Sequence" if what == "sequence" else "Provirus"      # the reference's log wording (nn_classification.py:333, 351, 407, 425)
-        # ---- encode (here: record the window -> sequence map; the windows themselves are streamed to the GPU below)
         if enc_skip:
             console.log(f"{enc_dir.name} was found. Skipping {what} encoding.")
         else:
             parsed = parsed_input if what == "sequence" else sequence.ParsedFasta(fasta, single_window, threads)
             index = _encode_stage(console, enc_dir, id_path, names_key, ids_key, what, is_main, parsed, classifier)
+        staged.append((parsed, index))
+
+    # ---- stage 2, every job: classify, write NPZ, clean up, write TSV (nn_classification.py:283-353, 355-425)
+    for (what, noun, fasta, enc_dir, id_path, names_key, ids_key, npz_path, tsv_path, must_have_windows), \
+            (enc_skip, cls_skip), (parsed, index) in zip(jobs, plan, staged):
+        names = preds = None
+        label = "Sequence" if what == "sequence" else "Provirus"      # the reference's log wording (nn_classification.py:333, 351, 407, 425)
         # ---- classify
         if cls_skip:
             console.log(f"{npz_path.name} was found. Skipping {what} classification.")
