@@ -72,8 +72,8 @@ constexpr int kWgSmem     = kWgSlab + 2048;                       //            
 // tensor memory (512 columns): two accumulators of kWgN columns, then the w_v weights (A operand of the TS-form tcgen05.mma):
 // fp16 pairs along k, 64 columns for the hi halves and 64 for the lo halves
 constexpr int kWgTmemW    = 2 * kWgN;                             // 384
-constexpr int kWgMmaSplit = 1;                                    // every tcgen05.mma of a unit is issued as this many column slices (N = 96): the gather's
-                                                                  // warp-level mma only gets the tensor pipe between two tcgen05.mma
+constexpr int kWgMmaSplit = 1;                                    // experiment: issue every tcgen05.mma of a unit as this many column slices (2 -> N = 96,
+                                                                  // more instruction boundaries for the gather's warp-level mma): measured neutral
 static_assert((kWgN / kWgMmaSplit) % 16 == 0 && ((kWgN / kWgMmaSplit) * 128) % 1024 == 0, "slices must be valid N and start on a swizzle atom");
 static_assert(kWgTmemW + 128 <= 512, "two accumulators + the weights must fit the 512 TMEM columns");
 static_assert(kWgSmem <= 232448, "wv_gather_kernel exceeds the 227 KB of shared memory a CTA may use");
@@ -84,7 +84,7 @@ static_assert(kWgEpiWarps == 4 && kWgWarps % 4 == 0 && kWgWarps >= 4, "one epilo
 struct WvGatherParams {
   float* q_out;                // [n][749][128]
   float out_scale;             // 1/32 (activation scale)
-  const int2* grp;             // [groups of all bands] {first entry slot, row inside the band | entries << 8}: the entries (<= 8) on one position
+  const int2* grp;             // [groups of all bands] {first entry slot, row inside the band | entries << 8}: the entries (<= 4) on one position
   const int32_t* band_gstart;  // [kNumBands + 1] first position group of every band
   const uint4* wfrag;          // [kGsSlots][2 K-halves][4 k-steps][4 tig] folded weights * 2^k as mma.m16n8k16 B fragments {hi b0, hi b1, lo b0, lo b1}: a lane reads the (b0, b1) pair of its column
   float gather_unscale;        // 1 / (power of two that moved the folded weights into fp16's normal range)
@@ -92,7 +92,7 @@ struct WvGatherParams {
   int n_windows, n_pad;        // n_pad = n rounded up to a multiple of 8
   int groups;                  // window groups per band = n_pad / 8
   int n_units;                 // kNumBands * groups
-  const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (balanced by the bands' entry counts)
+  const int32_t* cta_split;    // [gridDim.x + 1] unit range of every CTA (api.cu wv_split: near-equal unit counts)
   int experiment;              // timing experiments only (results become wrong): 32 = no gather work, 64 = no part_t stores, 128 = no q stores, 256 = gather reads its rows and weights but does no arithmetic, 1024 = no weight loads, 2048 = no ldmatrix
   const uint32_t* wv_t16;      // [2 hi/lo][128 cout][64] packed fp16 pairs of w_v^T: the A operand, copied into tensor memory once per CTA
   long long* dbg;              // optional [gridDim.x][8] cycle counters (nullptr = off), see tools/ab_stages.py --wvg-cycles
