@@ -131,6 +131,20 @@ def main():
         rows = [tf.io.parse_single_example(r, desc)["sequence"] for r in tf.data.TFRecordDataset(files)]
         toks[key] = np.stack(rows).astype(np.uint16)
     np.savez_compressed(gold / "run_default" / "encoded_tokens.npz", **toks)
+    # skip / restart scenarios in the same directory (log messages only): nothing changed; provirus NPZ lost; --restart;
+    # parameter change (--single-window, with --cleanup)
+    o = paths.GenomadOutputs("toy", out)
+    scen = {}
+
+    def logged(name, *args):
+        mod.main(fa, out, *args)
+        scen[name] = re.sub(r"^\[\d\d:\d\d:\d\d\] ", "", o.nn_classification_log.read_text(), flags=re.M)
+    logged("rerun_unchanged", False, 4, False, 1, False, False)
+    o.provirus_nn_classification_npz_output.unlink()
+    logged("provirus_npz_lost", False, 4, False, 1, False, False)
+    logged("restart", False, 4, True, 1, False, False)
+    logged("parameter_change_single_window_cleanup", True, 4, False, 1, False, True)
+    (gold / "scenario_logs.json").write_text(json.dumps(scen, indent=1) + "\n")
     # run 2: --single-window --cleanup into a fresh directory (same find-proviruses files)
     out2 = work / "out_single"
     shutil.copytree(gold / "input" / "toy_find_proviruses", out2 / "toy_find_proviruses")

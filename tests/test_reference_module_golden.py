@@ -122,23 +122,72 @@ def test_output_surface_matches_reference_module_run(gold, tmp_path):
         assert not utils.compare_executions(fa, {"single_window": not single}, gold / run / "toy_nn_classification.json")
 
 
-_SEQ = ("Encoded sequence data written to", "Sequences classified.", "Sequence classification in binary format written to",
-        "Deleting encoded sequence data.", "Sequence classification in tabular format written to")
-_PRO = ("Encoded provirus data written to", "Proviruses classified.", "Provirus classification in binary format written to",
-        "Deleting encoded provirus data.", "Provirus classification in tabular format written to")
+_EVENTS = (
+    ("executing", r"Executinggenomadnn-classification\."),
+    ("previous_execution_detected", r"Previousexecutiondetected"),
+    ("input_or_parameters_changed", r"Theinputfileortheparameterschanged"),
+    ("mkdir_module", r"Creatingthe[^.]*?toy_nn_classificationdirectory\."),
+    ("mkdir_encoded_sequences", r"Creatingthe[^.]*?toy_encoded_sequencesdirectory\."),
+    ("mkdir_encoded_proviruses", r"Creatingthe[^.]*?toy_encoded_provirusesdirectory\."),
+    ("skip_sequence_encoding", r"toy_encoded_sequenceswasfound\.Skippingsequenceencoding"),
+    ("skip_provirus_encoding", r"toy_encoded_proviruseswasfound\.Skippingprovirusencoding"),
+    ("encoded_sequences", r"Encodedsequencedatawrittento"),
+    ("encoded_proviruses", r"Encodedprovirusdatawrittento"),
+    ("skip_sequence_classification", r"toy_nn_classification\.npzwasfound\.Skippingsequenceclassification"),
+    ("skip_provirus_classification", r"toy_provirus_nn_classification\.npzwasfound\.Skippingprovirusclassification"),
+    ("sequences_classified", r"Sequencesclassified\."),
+    ("proviruses_classified", r"Provirusesclassified\."),
+    ("sequence_npz_written", r"Sequenceclassificationinbinaryformatwrittento"),
+    ("provirus_npz_written", r"Provirusclassificationinbinaryformatwrittento"),
+    ("delete_encoded_sequences", r"Deletingencodedsequencedata\."),
+    ("delete_encoded_proviruses", r"Deletingencodedprovirusdata\."),
+    ("sequence_tsv_written", r"Sequenceclassificationintabularformatwrittento"),
+    ("provirus_tsv_written", r"Provirusclassificationintabularformatwrittento"),
+    ("finished", r"geNomadnn-classificationfinished!"),
+)
 
 
-def _messages(text):
-    """Path-free log messages in order of appearance (rich wraps long lines; paths differ between the two runs)."""
-    keep = ("Executing genomad nn-classification",) + _SEQ + _PRO + ("geNomad nn-classification finished!",)
-    flat = " ".join(text.split())
-    return [k for _, k in sorted((flat.find(k), k) for k in keep if k in flat)]
+def _events(text):
+    """The module's log as a sequence of events: header panel and timestamps dropped, ALL white space removed (rich wraps long
+    lines, also inside paths), every message pattern located, ordered by position."""
+    import re
+    body = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith(("│", "╭", "╰")))
+    body = re.sub(r"^\[\d\d:\d\d:\d\d\] ", "", body, flags=re.M)
+    flat = re.sub(r"\s+", "", body)
+    found = [(m.start(), name) for name, pat in _EVENTS for m in re.finditer(pat, flat)]
+    return [name for _, name in sorted(found)]
+
+
+def _skip_restart_scenarios(gold, fa, out):
+    """Second and later runs in the same directory, against the reference module's logs of the same scenarios
+    (tests/golden/reference_module/scenario_logs.json): nothing changed -> every step skipped; the provirus NPZ lost -> only the
+    provirus classification is redone; --restart; parameter change (--single-window, --cleanup)."""
+    ref = json.loads((gold / "scenario_logs.json").read_text())
+    o = _paths.NNOutputs("toy", out)
+    watched = (o.nn_classification_npz_output, o.provirus_nn_classification_npz_output)
+
+    def run(name, *args):
+        before = {p.name: p.stat().st_mtime_ns for p in watched if p.exists()}
+        nn_classification.main(fa, out, *args)
+        mine, want = _events(o.nn_classification_log.read_text()), _events(ref[name])
+        assert mine == want, (name, mine, want)
+        return before, {p.name: p.stat().st_mtime_ns for p in watched if p.exists()}
+    b, a = run("rerun_unchanged", False, 4, False, 2, False, False)
+    assert a == b                                              # nothing rewritten
+    o.provirus_nn_classification_npz_output.unlink()
+    b, a = run("provirus_npz_lost", False, 4, False, 2, False, False)
+    assert a["toy_nn_classification.npz"] == b["toy_nn_classification.npz"] and "toy_provirus_nn_classification.npz" in a
+    run("restart", False, 4, True, 2, False, False)
+    run("parameter_change_single_window_cleanup", True, 4, False, 2, False, True)
+    assert not o.encoded_sequences_dir.exists() and not o.encoded_proviruses_dir.exists()
+    z = np.load(o.nn_classification_npz_output)
+    r = np.load(gold / "run_single_window_cleanup" / "toy_nn_classification.npz")
+    assert list(z["contig_names"]) == list(r["contig_names"]) and np.abs(z["predictions"] - r["predictions"]).max() <= 1e-4
 
 
 def _run_module_and_compare(gold, tmp_path):
     """genomad_b200.nn_classification.main on the golden input, both runs: same files, names, NPZ keys / dtypes, JSON, log messages;
     scores within 1e-4 of the reference module's, TSV equal up to one unit in the 4th decimal."""
-    import re
     for run, single in RUNS:
         work = tmp_path / run
         shutil.copytree(gold / "input", work)
@@ -176,9 +225,10 @@ def _run_module_and_compare(gold, tmp_path):
         got = json.loads((sub / "toy_nn_classification.json").read_text())
         ref = json.loads((d / "toy_nn_classification.json").read_text())
         assert list(got) == list(ref) and {k: v for k, v in got.items() if k != "start_time"} == {k: v for k, v in ref.items() if k != "start_time"}
-        log = re.sub(r"^\[\d\d:\d\d:\d\d\] ", "", (out / "toy_nn_classification.log").read_text(), flags=re.M)
-        mine, ref = _messages(log), _messages((d / "log_without_timestamps.txt").read_text())
-        assert mine == ref, (run, mine, ref)                   # same messages in the same order
+        mine, ref = _events((out / "toy_nn_classification.log").read_text()), _events((d / "log_without_timestamps.txt").read_text())
+        assert mine == ref and len(ref) >= 12, (run, mine, ref)          # same messages in the same order
+        if not single:
+            _skip_restart_scenarios(gold, work / "toy.fna", out)
 
 
 def test_module_host_logic_matches_reference_module_run(gold, tmp_path, weights_npz, monkeypatch):
