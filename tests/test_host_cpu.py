@@ -149,7 +149,7 @@ def _frag_halves(words):
     return w.view(np.uint16).reshape(w.shape + (2,)).view(np.float16).astype(np.float32)
 
 
-@pytest.mark.parametrize("kind", ["random", "one_position", "ends"])
+@pytest.mark.parametrize("kind", ["random", "one_position", "ends", "one_band", "band_edges"])
 def test_patch_packing_for_the_fused_gather(kind):
     """Host logic of the fused IGLOO kernel (csrc/api.cu pack_patches; kernel side csrc/wv_gather.cuh): every (patch, k) entry
     lands in exactly one position group of <= 4 entries that share a position inside the right band, and the mma B fragments
@@ -161,8 +161,13 @@ def test_patch_packing_for_the_fused_gather(kind):
         patches = rng.integers(0, 5997, size=(2100, 4), dtype=np.int32)
     elif kind == "one_position":
         patches = np.full((2100, 4), 3001, np.int32)
-    else:
+    elif kind == "ends":
         patches = np.tile(np.asarray([0, 1, 5995, 5996], np.int32), (2100, 1))
+    elif kind == "one_band":                                       # 8,400 entries on the 24 positions of one band: 350 per position
+        patches = (2400 + rng.integers(0, 24, size=(2100, 4))).astype(np.int32)
+    else:                                                          # only first / last positions of bands, incl. the short last band
+        edges = np.array([0, 23, 24, 47, 5975, 5976, 5996, 5995, 2399, 2400], np.int32)
+        patches = edges[rng.integers(0, len(edges), size=(2100, 4))]
     w_mult = (rng.standard_normal((2100, 4, 128)) * 0.05).astype(np.float32)
     w_mult[7] = 0.0                                               # an all-zero patch
     w_mult[8, 1, :5] = [1e-9, -3e-7, 2.5, -1e-4, 6e-6]              # a wide dynamic range inside one entry
