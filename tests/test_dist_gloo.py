@@ -112,6 +112,9 @@ def _driver_worker(rank, world, port, tmp):
     nn_classification.main(fa, out, False, 128, False, 2, False, False)          # fresh run
     if rank == 0:
         first = np.load(o.nn_classification_npz_output)["predictions"].copy()
+        pv = np.load(o.provirus_nn_classification_npz_output)                    # the provirus twin ran on both ranks as well
+        assert pv["provirus_names"].tolist() == ["c0|provirus_1_9000", "c3|provirus_101_6500"] and pv["predictions"].shape == (2, 3)
+        assert np.load(o.provirus_window_id_output)["provirus_ids"].tolist() == [0, 0, 1]
     nn_classification.main(fa, out, False, 128, False, 2, False, False)          # skip run: nobody may enter the collective
     dist.barrier()
     if rank == 0:
@@ -134,6 +137,19 @@ def test_world2_module_driver_rank0_decides(tmp_path):
         for i, ln in enumerate([20000, 6100, 3000, 47000, 9000]):
             s = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, ln)].tobytes().decode()
             fh.write(f">c{i}\n" + "\n".join(s[k:k + 70] for k in range(0, ln, 70)) + "\n")
+    # a finished find-proviruses run on the same input: rank 0 alone detects it and broadcasts the decision
+    from genomad_b200 import _paths, utils
+    out = tmp_path / "out"
+    out.mkdir()
+    o = _paths.NNOutputs("in", out)
+    o.find_proviruses_dir.mkdir()
+    utils.write_execution_info("find_proviruses", tmp_path / "in.fna", {}, o.find_proviruses_execution_info)
+    pv = {"c0|provirus_1_9000": 9000, "c3|provirus_101_6500": 6400}
+    o.find_proviruses_output.write_text("seq_name\tx\n" + "".join(f"{k}\t1\n" for k in pv))
+    o.find_proviruses_nucleotide_output.write_text("".join(
+        f">{k}\n" + np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].tobytes().decode() + "\n" for k, n in pv.items()))
+    o.find_proviruses_proteins_output.write_text("")
+    o.find_proviruses_genes_output.write_text("")
     mp.spawn(_driver_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     first = np.load(tmp_path / "first.npy")
     # single-process run of the same stub pipeline gives the same per-contig means (sharding is invisible)
