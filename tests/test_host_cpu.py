@@ -243,6 +243,27 @@ def test_patch_packing_for_the_fused_gather(kind):
         assert np.abs(got - want).max() <= tol, (kind, gi, np.abs(got - want).max(), tol)
 
 
+def test_integration_md_ctypes_stub(repo_root, weights_npz):
+    """The reference-side binding shown in INTEGRATION.md (level 2) is executable as printed: it binds libgnm.so, fills
+    gnm_weights through genomad_b200.weights, and -- on a box without a GPU -- gnm_create fails loudly through
+    gnm_last_error (there is no CPU fallback); with a GPU it classifies."""
+    import torch
+    text = (repo_root / "INTEGRATION.md").read_text()
+    block = text[text.index("```python\nimport ctypes as C, numpy as np"):]
+    block = block[len("```python\n"):block.index("\n```")]
+    assert "class GnmModel" in block and "gnm_classify_host" in block
+    block = block.replace('C.CDLL("libgnm.so")', f'C.CDLL({str(repo_root / "genomad_b200" / "libgnm.so")!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns["GnmModel"](weights_npz, 8)
+    else:
+        m = ns["GnmModel"](weights_npz, 8)
+        p = m.predict(np.full((2, 6000), ord("A"), np.uint8))
+        assert p.shape == (2, 3) and np.allclose(p.sum(1), 1, atol=1e-5)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
