@@ -9,7 +9,8 @@ Nothing under ``genomad_b200/`` imports it.
 
 What is pinned and what is not
 ------------------------------
-* Tokenizer / windowing / FASTA reader (``oracle/tokenizer.py``; pure NumPy, there is no C restatement):
+* Tokenizer / windowing / FASTA reader (``oracle/tokenizer.py``, NumPy; plus ``oracle/tokenizer_c.c``, a plain-C
+  restatement of the tokenizer and the window rules built by ``oracle/build_c.py`` / ``__graft_entry__.build()``):
   PINNED.  They are checked against golden vectors produced by running the *real*
   reference code (``/root/reference/genomad/sequence.py`` under numba) in the build
   container; generator: ``tests/golden/make_golden.py``, vectors: ``tests/golden/*.npz|json``.

@@ -37,6 +37,40 @@ def test_tokenizer_closed_form_matches_reference_batch(enc, golden_dir):
         assert T.tokenize_dna_literal(a[i].tobytes()) == ref[i].tolist()
 
 
+def test_c_oracle_tokenizer_and_window_rules(enc, golden_dir):
+    """oracle/tokenizer_c.c (plain C, built with gcc) against the vectors made by the real reference code, and against the NumPy
+    closed form: adversarial strings of any length, the seeded batch, and the reference module's own encoding-stage tokens."""
+    from oracle import build_c as OC
+    for case in enc["tokenize"]:
+        assert OC.tokenize(case["seq"].encode("ascii")) == case["tokens"], case["seq"]
+    ref = np.load(golden_dir / "encoder_batch_tokens.npz")["tokens"]
+    raws = enc["batch"]["raw"]
+    a = np.frombuffer(b"".join(r.upper().encode("ascii").ljust(6000, b"N") for r in raws), np.uint8).reshape(-1, 6000)
+    assert np.array_equal(OC.tokenize_windows(a), ref)
+    rng = np.random.default_rng(9)
+    r = np.frombuffer(b"ACGTNRacgtn-", np.uint8)[rng.integers(0, 12, (64, 6000))]
+    assert np.array_equal(OC.tokenize_windows(r), T.tokenize_windows(r))
+    # FASTA -> windows -> tokens of the reference module run (N rule, short tail, lower case, IUPAC), both window modes
+    toks = np.load(golden_dir / "reference_module" / "run_default" / "encoded_tokens.npz")
+    ids = np.load(golden_dir / "reference_module" / "run_default" / "toy_seq_window_id.npz")["contig_ids"]
+    for single in (False, True):
+        wins, got_ids = [], []
+        for cid, (_, seq) in enumerate(T.read_fasta(golden_dir / "reference_module" / "input" / "toy.fna", strip_n=True)):
+            raw = seq.encode("ascii")
+            starts, lengths = OC.window_plan(raw, single)
+            py = [w for n, w in enumerate(T.seq_windows(seq, max_windows=1 if single else None)) if not (n > 0 and w.count("N") > 4000)]
+            assert [raw[s:s + l].decode() for s, l in zip(starts, lengths)] == py
+            for s, l in zip(starts, lengths):
+                wins.append(raw[s:s + l].upper().ljust(6000, b"N"))
+                got_ids.append(cid)
+        arr = np.frombuffer(b"".join(wins), np.uint8).reshape(-1, 6000)
+        if single:
+            first = np.concatenate([[0], np.flatnonzero(np.diff(ids)) + 1])
+            assert np.array_equal(OC.tokenize_windows(arr), toks["sequences"][first])
+        else:
+            assert got_ids == ids.tolist() and np.array_equal(OC.tokenize_windows(arr), toks["sequences"])
+
+
 def test_seq_windows_lengths(enc):
     for case in enc["windows"]:
         s = "A" * case["len"]
