@@ -402,21 +402,6 @@ def test_live_igloo_weights_320_windows_vs_oracle(golden_dir, shipped):
     print(f"live IGLOO weights: max |dp| vs fp32 oracle = {d32.max():.2e}, vs fp64 = {d64.max():.2e}")
 
 
-def test_cuda_vs_reference_graph_golden(golden_dir, clf, clf_syn):
-    """The CUDA path against vectors of the REFERENCE'S OWN model definition (genomad/neural_network/{model,igloo}.py executed on
-    the NumPy stand-in tests/golden/keras_shim.py, fp64; generator tests/golden/make_reference_graph_golden.py) -- not via the
-    oracle: 24 windows (N / IUPAC windows and the worst-case families included), shipped weights and synthetic O(1) IGLOO weights."""
-    g = np.load(golden_dir / "reference_graph_golden.npz")
-    a = torch.from_numpy(g["windows"]).cuda()
-    for key, c in (("shipped", clf), ("synthetic", clf_syn)):
-        p = c.predict_ascii(a).cpu().numpy()
-        ref = g[key + "_fp64"]
-        d = np.abs(p - ref).max()
-        assert d <= TOL, (key, d)
-        assert np.array_equal(p.argmax(1), ref.argmax(1)), key
-        print(f"CUDA vs reference graph ({key} weights): max |dp| = {d:.2e}")
-
-
 # ------------------------------------------------------------------------------------------ provirus twin + skip / restart on the GPU
 def test_module_provirus_twin_skip_and_restart(tmp_path, shipped):
     """SURVEY 8(f) rank 2 with the REAL classifier: the provirus twin (reference nn_classification.py:248-281, 355-425),
@@ -604,3 +589,19 @@ def test_adversarial_patch_sets(shipped):
             c.close()
         assert np.abs(p - ref).max() <= TOL, (name, np.abs(p - ref).max())
         assert np.array_equal(p.argmax(1), ref.argmax(1)), name
+
+
+# ------------------------------------------------------------------------------------------ vectors of the reference's own model code
+def test_cuda_vs_reference_graph_golden(golden_dir, clf, clf_syn):
+    """The CUDA path against vectors of the REFERENCE'S OWN model definition (genomad/neural_network/{model,igloo}.py executed on
+    the NumPy stand-in tests/golden/keras_shim.py, fp64; generator tests/golden/make_reference_graph_golden.py) -- not via the
+    oracle: 24 windows (N / IUPAC windows and the worst-case families included), shipped weights and synthetic O(1) IGLOO weights."""
+    g = np.load(golden_dir / "reference_graph_golden.npz")
+    a = torch.from_numpy(g["windows"]).cuda()
+    for key, c in (("shipped", clf), ("synthetic", clf_syn)):
+        p = c.predict_ascii(a).cpu().numpy()
+        ref = g[key + "_fp64"]
+        d = np.abs(p - ref).max()
+        assert d <= TOL, (key, d)
+        assert np.array_equal(p.argmax(1), ref.argmax(1)), key
+        print(f"CUDA vs reference graph ({key} weights): max |dp| = {d:.2e}")
