@@ -71,6 +71,36 @@ def test_c_oracle_tokenizer_and_window_rules(enc, golden_dir):
             assert got_ids == ids.tolist() and np.array_equal(OC.tokenize_windows(arr), toks["sequences"])
 
 
+def test_c_oracle_matches_literal_loop_on_random_strings():
+    """Property check: the C tokenizer == the literal transcription of the reference loop, for strings of any length
+    (0 .. 40; the Python-slice corner below 4 bases included) over an alphabet with invalid and lower-case bytes."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import build_c as OC
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.text(alphabet="ACGTNacgtR-", min_size=0, max_size=40))
+    def check(sq):
+        b = sq.encode("ascii")
+        assert OC.tokenize(b) == T.tokenize_dna_literal(b)
+    check()
+    # window plan == the Python generator + N rule on structured random sequences
+    rng = np.random.default_rng(4)
+    for _ in range(60):
+        n = int(rng.integers(1, 30000))
+        sq = bytearray(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)].tobytes())
+        for _ in range(int(rng.integers(0, 3))):                      # N runs, some longer than 4,000
+            a = int(rng.integers(0, n)); ln = int(rng.integers(1, 7000))
+            sq[a:a + ln] = b"N" * len(sq[a:a + ln])
+        sq = bytes(sq).strip(b"N")
+        if not sq:
+            continue
+        for single in (False, True):
+            starts, lengths = OC.window_plan(sq, single)
+            s = sq.decode()
+            py = [w for k, w in enumerate(T.seq_windows(s, max_windows=1 if single else None)) if not (k > 0 and w.count("N") > 4000)]
+            assert [s[a:a + l] for a, l in zip(starts, lengths)] == py
+
+
 def test_seq_windows_lengths(enc):
     for case in enc["windows"]:
         s = "A" * case["len"]
